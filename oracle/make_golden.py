@@ -1,0 +1,168 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (fp32, CPU) in the build container.
+
+TEST INFRASTRUCTURE.  Run as `python -m oracle.make_golden` from the repo root; needs
+/root/reference (oracle/ref_loader.py).  Inputs and weights are NOT stored: they are regenerated
+from seeds by `temporalalignnet_b200.synth` (numpy PCG64, order-independent); each fixture
+records a float64 checksum of every input so RNG drift is detected instead of silently
+mis-comparing.  Outputs are the reference's own tensors.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import load_reference  # noqa: E402
+from temporalalignnet_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (model kwargs, batch kwargs)
+CASES = {
+    # BASELINE.json configs[0]: E1D1 len=32 d=512 batch=4 (the correctness gate)
+    "g1_e1d1_T32_B4": dict(E=1, D=1, B=4, T=32, N=4, pad_video_every=0, use_text_pos_enc=0, head=0),
+    # ragged text, padded video suffix, text pos-enc, alignability head, deeper stacks
+    "g2_e2d3_T24_B3": dict(E=2, D=3, B=3, T=24, N=5, pad_video_every=2, use_text_pos_enc=1, head=1),
+    # the paper's stage count at toy size (E6D6), joint length T+N = 72 like config 2
+    "g3_e6d6_T64_B2": dict(E=6, D=6, B=2, T=64, N=8, pad_video_every=0, use_text_pos_enc=0, head=0),
+}
+
+
+def checksum(a) -> float:
+    a = np.asarray(a, dtype=np.float64).ravel()
+    return float((a * (1.0 + (np.arange(a.size) % 7))).sum())
+
+
+def loss_args(**kw):
+    d = dict(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep",
+             loss_threshold=0.0, use_alignability_head=0, optim_policy="default")
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def build_reference_model(tan, E, D, use_text_pos_enc, head, seed=888):
+    m = tan.TemporalAligner(num_encoder_layers=E, num_decoder_layers=D, sim="cos",
+                            language_model="word2vec", pos_enc="learned",
+                            use_text_pos_enc=use_text_pos_enc, return_dual_feature=1,
+                            random_pos_start=0, use_alignability_head=head)
+    sd = synth.make_state_dict(E, D, use_alignability_head=bool(head), seed=seed)
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.startswith("bert.") for k in missing), (missing, unexpected)
+    m.eval()
+    return m, sd
+
+
+def run_case(name, cfg):
+    tfm, tan, ref_loss = load_reference()
+    m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], cfg["head"])
+    batch = synth.make_batch(cfg["B"], cfg["T"], cfg["N"], pad_video_every=cfg["pad_video_every"])
+    video = torch.from_numpy(batch["video"])
+    text = torch.from_numpy(batch["text"])
+    vpm = torch.from_numpy(batch["video_padding_mask"])
+    tpm = torch.from_numpy(batch["text_padding_mask"])
+    out = {"in_checksum_video": checksum(batch["video"]), "in_checksum_text": checksum(batch["text"]),
+           "in_checksum_weights": sum(checksum(v) for v in sd.values()),
+           "in_start": np.array([x for s in batch["start"] for x in s]),
+           "in_end": np.array([x for s in batch["end"] for x in s])}
+    sub = 4 if cfg["T"] > 32 else 1              # keep fixtures small: every 4th frame of long clips
+    with torch.no_grad():
+        res = m(video, text, vpm, tpm, None)
+        for k, v in res.items():
+            out["fwd_" + k] = v.numpy()[:, :, ::sub] if k == "dual_feature_video" else v.numpy()
+        out["feat_subsample"] = np.array(sub)
+        out["visual_feature"] = m.get_visual_feature(video, vpm).numpy()[:, :, ::sub]
+        t_in = (m.get_textual_feature_with_time(text, None) if cfg["use_text_pos_enc"]
+                else m.get_textual_feature(text))
+        jv, jt = m.get_joint_feature(video, vpm, t_in, tpm)
+        out["joint_video"] = jv.numpy()[:, :, ::sub]
+        out["joint_text"] = jt.numpy()
+        out["sim_dual_eval"] = m.get_text_visual_sim_dual(video, text).numpy()
+        out["sim_joint_eval"] = m.get_text_visual_sim_joint(video, text).numpy()
+        # positional-table interpolation path (eval 'global' method, eval_zeroshot_align.py:208-209)
+        k_from = max(cfg["T"] // 2, 2)
+        out["interp_from"] = np.array(k_from)
+        out["sim_dual_eval_interp"] = m.get_text_visual_sim_dual(video, text, k_from).numpy()
+        out["sim_joint_eval_interp"] = m.get_text_visual_sim_joint(video, text, k_from).numpy()
+    # loss + gradient w.r.t. logits (fp32)
+    input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
+    ld = res["logits_dual"].clone().requires_grad_(True)
+    lj = res["logits_joint"].clone().requires_grad_(True)
+    logits = dict(res)
+    logits["logits_dual"], logits["logits_joint"] = ld, lj
+    loss = ref_loss.get_loss(input_data, video, text, vpm.float(), tpm.float(), logits, loss_args(), None)
+    loss["loss"].backward()
+    for k, v in loss.items():
+        out["loss_" + k] = np.array(float(v))
+    out["grad_logits_dual"] = ld.grad.numpy()
+    out["grad_logits_joint"] = lj.grad.numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), **{k: np.asarray(v) for k, v in out.items()})
+    print(name, {k: float(v) for k, v in loss.items()})
+
+
+def block_weights(module, tag, seed=888):
+    """Seeded (numpy, order-independent) weights for a bare encoder/decoder stack: matrices
+    N(0, 0.05), vectors N(0.5, 0.2).  tests/ regenerate them with the same rule."""
+    return {k: torch.from_numpy(synth._normal(f"{tag}.{k}", seed, tuple(v.shape),
+                                              0.05 if v.dim() > 1 else 0.2, 0.0 if v.dim() > 1 else 0.5))
+            for k, v in module.state_dict().items()}
+
+
+def run_blocks():
+    """Golden vectors for the building blocks at shapes TAN itself never uses: width 768 / 12 heads
+    (BASELINE config 4) and the unused TemporalDecoder (model/tfm_model.py:59-103)."""
+    tfm, tan, ref_loss = load_reference()
+    out = {}
+    g = torch.Generator().manual_seed(888)
+    for tag, width, heads, layers, L, B in (("enc768", 768, 12, 2, 20, 2), ("enc128", 128, 2, 3, 37, 3)):
+        enc = tfm.TemporalEncoder(width, layers, heads).eval()
+        enc.load_state_dict(block_weights(enc, tag))
+        x = torch.randn(L, B, width, generator=g)
+        kpm = torch.zeros(B, L, dtype=torch.bool)
+        kpm[0, L - 3:] = True
+        with torch.no_grad():
+            st = enc(x, kpm)
+        out[tag + "_x"] = x.numpy()
+        out[tag + "_kpm"] = kpm.numpy()
+        out[tag + "_out"] = torch.stack(st).numpy()           # [S, L, B, C]
+    dec = tfm.TemporalDecoder(128, 2, 2).eval()
+    dec.load_state_dict(block_weights(dec, "dec"))
+    x = torch.randn(10, 2, 128, generator=g)
+    mem = torch.randn(12, 2, 128, generator=g)
+    tk = torch.zeros(2, 10, dtype=torch.bool); tk[1, 8:] = True
+    mk = torch.zeros(2, 12, dtype=torch.bool); mk[0, 9:] = True
+    with torch.no_grad():
+        st = dec(x, mem, tk, mk)
+    out.update(dec_x=x.numpy(), dec_mem=mem.numpy(), dec_tk=tk.numpy(), dec_mk=mk.numpy(),
+               dec_out=torch.stack(st).numpy())
+    # the reference's only executable known-answer (train/loss.py:19-20)
+    out["circulant_012"] = ref_loss.circulant(torch.tensor([0, 1, 2]), dim=0).numpy()
+    out["sine_pos_16x8"] = tfm.get_position_embedding_sine(8, 16).numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_blocks.npz"), **out)
+    print("g_blocks", out["circulant_012"].tolist())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.manual_seed(888)
+    np.random.seed(888)
+    torch.set_grad_enabled(True)
+    for name, cfg in CASES.items():
+        if a.only and a.only != name:
+            continue
+        run_case(name, cfg)
+    if not a.only or a.only == "g_blocks":
+        run_blocks()
+
+
+if __name__ == "__main__":
+    main()

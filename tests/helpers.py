@@ -1,0 +1,49 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import os
+
+import numpy as np
+import torch
+
+from temporalalignnet_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# must mirror oracle/make_golden.py:CASES
+CASES = {
+    "g1_e1d1_T32_B4": dict(E=1, D=1, B=4, T=32, N=4, pad_video_every=0, use_text_pos_enc=0, head=0),
+    "g2_e2d3_T24_B3": dict(E=2, D=3, B=3, T=24, N=5, pad_video_every=2, use_text_pos_enc=1, head=1),
+    "g3_e6d6_T64_B2": dict(E=6, D=6, B=2, T=64, N=8, pad_video_every=0, use_text_pos_enc=0, head=0),
+}
+
+
+def checksum(a) -> float:
+    a = np.asarray(a, dtype=np.float64).ravel()
+    return float((a * (1.0 + (np.arange(a.size) % 7))).sum())
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+def case_inputs(name):
+    """(cfg, state_dict numpy, batch) regenerated from seeds + drift check against the fixture."""
+    cfg = CASES[name]
+    g = load_golden(name)
+    sd = synth.make_state_dict(cfg["E"], cfg["D"], use_alignability_head=bool(cfg["head"]))
+    batch = synth.make_batch(cfg["B"], cfg["T"], cfg["N"], pad_video_every=cfg["pad_video_every"])
+    assert abs(checksum(batch["video"]) - float(g["in_checksum_video"])) < 1e-6, "synthetic RNG drifted"
+    assert abs(checksum(batch["text"]) - float(g["in_checksum_text"])) < 1e-6
+    assert abs(sum(checksum(v) for v in sd.values()) - float(g["in_checksum_weights"])) < 1e-6
+    return cfg, sd, batch, g
+
+
+def rel_fro(a, b):
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def max_abs(a, b):
+    a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
+    return float((a - b).abs().max())

@@ -1,0 +1,143 @@
+"""Pins the CPU oracle (oracle/tan_oracle.py) against outputs of the UNMODIFIED reference:
+the committed fixtures (tests/golden, made by oracle/make_golden.py) always, and the live
+reference modules when /root/reference exists (build container only)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tan_oracle as O
+from oracle.ref_loader import reference_available
+from temporalalignnet_b200 import synth
+from tests.helpers import CASES, case_inputs, load_golden, max_abs
+
+FP32_TOL = 2e-5   # fp32 reassociation noise between two CPU evaluations of the same math
+
+
+def _run_oracle(cfg, sd, batch):
+    orc = O.TanOracle(sd, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"],
+                      use_alignability_head=cfg["head"])
+    video = torch.from_numpy(batch["video"])
+    text = torch.from_numpy(batch["text"])
+    out = orc.forward(video, text, batch["video_padding_mask"], batch["text_padding_mask"])
+    return orc, out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_reference_fixture(name):
+    cfg, sd, batch, g = case_inputs(name)
+    orc, out = _run_oracle(cfg, sd, batch)
+    sub = int(g["feat_subsample"])
+    assert max_abs(out["logits_dual"], g["fwd_logits_dual"]) < FP32_TOL
+    assert max_abs(out["logits_joint"], g["fwd_logits_joint"]) < FP32_TOL
+    assert max_abs(out["dual_feature_video"][:, :, ::sub], g["fwd_dual_feature_video"]) < FP32_TOL
+    assert max_abs(out["dual_feature_text"], g["fwd_dual_feature_text"]) < FP32_TOL
+    if cfg["head"]:
+        assert max_abs(out["dual_logits_alignability"], g["fwd_dual_logits_alignability"]) < FP32_TOL
+        assert max_abs(out["joint_logits_alignability"], g["fwd_joint_logits_alignability"]) < 1e-4
+    video = torch.from_numpy(batch["video"])
+    text = torch.from_numpy(batch["text"])
+    vpm = torch.from_numpy(batch["video_padding_mask"])
+    vf = orc.get_visual_feature(video, vpm)
+    assert max_abs(vf[:, :, ::sub], g["visual_feature"]) < 2e-4   # un-normalised features, |x| ~ 1-10
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_eval_sims_match_reference_fixture(name):
+    cfg, sd, batch, g = case_inputs(name)
+    orc = O.TanOracle(sd, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"],
+                      use_alignability_head=cfg["head"])
+    video = torch.from_numpy(batch["video"])
+    text = torch.from_numpy(batch["text"])
+    k = int(g["interp_from"])
+    assert max_abs(orc.get_text_visual_sim_dual(video, text), g["sim_dual_eval"]) < FP32_TOL
+    assert max_abs(orc.get_text_visual_sim_joint(video, text), g["sim_joint_eval"]) < FP32_TOL
+    assert max_abs(orc.get_text_visual_sim_dual(video, text, k), g["sim_dual_eval_interp"]) < FP32_TOL
+    assert max_abs(orc.get_text_visual_sim_joint(video, text, k), g["sim_joint_eval_interp"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_loss_matches_reference_fixture(name):
+    cfg, sd, batch, g = case_inputs(name)
+    ld = torch.from_numpy(g["fwd_logits_dual"]).requires_grad_(True)
+    lj = torch.from_numpy(g["fwd_logits_joint"]).requires_grad_(True)
+    loss = O.get_loss_init(ld, lj, batch["start"], batch["end"], batch["text_padding_mask"])
+    for k in ("loss", "loss-dual", "loss-joint"):
+        assert abs(float(loss[k]) - float(g["loss_" + k])) < 1e-5 * abs(float(g["loss_" + k])), k
+    loss["loss"].backward()
+    assert max_abs(ld.grad, g["grad_logits_dual"]) < 1e-6
+    assert max_abs(lj.grad, g["grad_logits_joint"]) < 1e-6
+
+
+def _block_sd(prefix_tag, keys_shapes, seed=888):
+    return {k: synth._normal(f"{prefix_tag}.{k}", seed, shape, 0.05 if len(shape) > 1 else 0.2,
+                             0.0 if len(shape) > 1 else 0.5) for k, shape in keys_shapes.items()}
+
+
+def _enc_shapes(width, layers, dec=False):
+    d = {}
+    for i in range(layers):
+        p = f"resblocks.{i}."
+        names = ["attn"] + (["self_attn"] if dec else [])
+        for a in names:
+            d[p + a + ".in_proj_weight"] = (3 * width, width)
+            d[p + a + ".in_proj_bias"] = (3 * width,)
+            d[p + a + ".out_proj.weight"] = (width, width)
+            d[p + a + ".out_proj.bias"] = (width,)
+        for ln in ["ln_1", "ln_2"] + (["ln_3"] if dec else []):
+            d[p + ln + ".weight"] = (width,)
+            d[p + ln + ".bias"] = (width,)
+        d[p + "mlp.c_fc.weight"] = (4 * width, width)
+        d[p + "mlp.c_fc.bias"] = (4 * width,)
+        d[p + "mlp.c_proj.weight"] = (width, 4 * width)
+        d[p + "mlp.c_proj.bias"] = (width,)
+    return d
+
+
+@pytest.mark.parametrize("tag,width,heads,layers", [("enc768", 768, 12, 2), ("enc128", 128, 2, 3)])
+def test_encoder_blocks_match_reference_fixture(tag, width, heads, layers):
+    g = load_golden("g_blocks")
+    sd = {"e." + k: torch.from_numpy(v) for k, v in _block_sd(tag, _enc_shapes(width, layers)).items()}
+    x = torch.from_numpy(g[tag + "_x"]).transpose(0, 1)          # [L,B,C] -> [B,L,C]
+    kpm = torch.from_numpy(g[tag + "_kpm"])
+    st = O.encoder_stack(x, kpm, sd, "e", layers, heads)
+    got = torch.stack(st).permute(0, 2, 1, 3)                     # [S,B,L,C] -> [S,L,B,C]
+    assert max_abs(got, g[tag + "_out"]) < 5e-4 * float(np.abs(g[tag + "_out"]).max())
+
+
+def test_decoder_blocks_match_reference_fixture():
+    g = load_golden("g_blocks")
+    sd = {"d." + k: torch.from_numpy(v) for k, v in _block_sd("dec", _enc_shapes(128, 2, dec=True)).items()}
+    x = torch.from_numpy(g["dec_x"]).transpose(0, 1)
+    mem = torch.from_numpy(g["dec_mem"]).transpose(0, 1)
+    st = O.decoder_stack(x, mem, torch.from_numpy(g["dec_tk"]), torch.from_numpy(g["dec_mk"]), sd, "d", 2, 2)
+    got = torch.stack(st).permute(0, 2, 1, 3)
+    assert max_abs(got, g["dec_out"]) < 5e-4 * float(np.abs(g["dec_out"]).max())
+
+
+def test_reference_known_answer_circulant():
+    """train/loss.py:19-20 -- the reference's only executable golden vector."""
+    g = load_golden("g_blocks")
+    assert g["circulant_012"].tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference only exists in the build container")
+def test_oracle_vs_live_reference_random_pos_start():
+    """Replays the reference's three np.random.randint draws (model/tan_model.py:163,:224,:195)."""
+    from oracle.make_golden import build_reference_model
+    from oracle.ref_loader import load_reference
+    _, tan, _ = load_reference()
+    cfg = dict(E=2, D=2, use_text_pos_enc=1, head=0)
+    m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], cfg["head"])
+    m.random_pos_start = 1
+    batch = synth.make_batch(2, 16, 4, seed=5)
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+    np.random.seed(123)
+    with torch.no_grad():
+        ref = m(video, text, vpm, tpm, None)
+    np.random.seed(123)
+    draws = (np.random.randint(0, 8), np.random.randint(0, 2), np.random.randint(0, 8))
+    orc = O.TanOracle(sd, 2, 2, use_text_pos_enc=1)
+    out = orc.forward(video, text, vpm, tpm, pos_starts=draws)
+    assert max_abs(out["logits_dual"], ref["logits_dual"]) < FP32_TOL
+    assert max_abs(out["logits_joint"], ref["logits_joint"]) < FP32_TOL
