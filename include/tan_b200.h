@@ -1,0 +1,200 @@
+/* tan_b200.h -- C ABI of the B200-native TAN hot path (libtan_b200.so).
+ *
+ * The reference (TengdaHan/TemporalAlignNet) is pure Python on PyTorch and has no FFI of its own;
+ * every arithmetic step of its hot path is a torch library call.  Each entry point below replaces
+ * one group of those call sites (cited per function, paths relative to the reference root).  The
+ * Python classes in temporalalignnet_b200/ (same names / arguments / state-dict keys as the
+ * reference's TemporalAligner, TemporalEncoder, get_loss) bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - bf16 tensors are passed as `const void*` / `void*` (raw __nv_bfloat16 storage), row-major,
+ *     innermost dimension contiguous; `ld*` arguments are row pitches in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; no call allocates, synchronises or uses the
+ *     default stream implicitly; every call is re-entrant per stream;
+ *   - return value: TAN_OK (0) or a negative TAN_ERR_* code; `tan_last_error_string()` gives a
+ *     thread-local human-readable message.  Shape violations are reported, never "fixed up".
+ *   - the library only contains sm_100a code: on any other device every compute entry point
+ *     returns TAN_ERR_ARCH.  There is no CPU path.
+ */
+#ifndef TAN_B200_H_
+#define TAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* exported symbols (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define TAN_API __attribute__((visibility("default")))
+#else
+#define TAN_API
+#endif
+
+#define TAN_OK 0
+#define TAN_ERR_SHAPE (-1)     /* unsupported / inconsistent dimensions or alignment */
+#define TAN_ERR_ARCH (-2)      /* device is not sm_100 */
+#define TAN_ERR_WORKSPACE (-3) /* workspace pointer null or too small */
+#define TAN_ERR_CUDA (-4)      /* a CUDA runtime / driver call failed (see error string) */
+#define TAN_ERR_ARG (-5)       /* null pointer or invalid flag */
+
+/* Epilogue activation for tan_linear_bf16. */
+#define TAN_ACT_NONE 0
+#define TAN_ACT_QUICKGELU 1 /* x * sigmoid(1.702 x), model/tfm_model.py:11-13 */
+
+/* ---- library ------------------------------------------------------------------------------- */
+
+/* ABI version of this header (bumped on any signature change). */
+TAN_API int tan_abi_version(void);
+/* Thread-local message for the last non-zero return code on this thread. */
+TAN_API const char* tan_last_error_string(void);
+/* TAN_OK if the current device is sm_100 (B200), TAN_ERR_ARCH otherwise, TAN_ERR_CUDA if no device. */
+TAN_API int tan_device_check(void);
+
+/* ---- dtype conversion ------------------------------------------------------------------------ */
+
+/* out[i] = bf16(in[i]), i < n.  Replaces the implicit fp32->half cast torch autocast inserts in
+ * front of every F.linear under train/main.py:81.  n % 8 == 0, 16-byte aligned pointers. */
+TAN_API int tan_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
+
+/* ---- GEMM (+ fused epilogue) ----------------------------------------------------------------- */
+
+/* out = act(A @ W^T + bias) [+ residual]
+ *   A   [M, K] bf16 (lda), W [N, K] bf16 (nn.Linear weight layout, ldw), bias [N] fp32 or NULL,
+ *   residual [M, N] fp32 (ldr) or NULL (may alias out_f32: each element is read before written),
+ *   out_f32 [M, N] fp32 (ldo_f32) and/or out_bf16 [M, N] bf16 (ldo_bf16); at least one non-NULL.
+ * tcgen05.mma (bf16 in, fp32 accumulate in TMEM), operands staged by TMA with 128-byte swizzle.
+ * Requirements: K % 64 == 0, N % 32 == 0, lda/ldw % 8 == 0, 16-byte aligned bases.
+ * Replaces F.linear at: model/tan_model.py:155,:187,:233 (pre-projections), torch
+ * nn/functional.py `_in_projection_packed` + out_proj reached from model/tfm_model.py:32 (QKV and
+ * output projections, residual add of :36), model/tfm_model.py:23-27,:37 (c_fc + QuickGELU,
+ * c_proj + residual). */
+TAN_API int tan_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                    const float* residual, int64_t ldr, float* out_f32, int64_t ldo_f32,
+                    void* out_bf16, int64_t ldo_bf16, int M, int N, int K, int act, void* stream);
+
+/* ---- LayerNorm (+ positional add, scatter, L2-normalised stage features) ---------------------- */
+
+/* Row-wise LayerNorm over the last dimension with optional fused extras.  For input row r
+ * (0 <= r < rows), with b = r / L_in and l = r % L_in:
+ *     y = LN(in[r]) * gamma + beta                (gamma == NULL: y = in[r], no normalisation)
+ *     y += add[(l % add_rows)]                     (add != NULL; fp32 [add_rows, d])
+ *     dst = b * L_out + l_off + l
+ *     out_f32[dst] = y ; out_bf16[dst] = bf16(y)   (each optional)
+ *   stage emission (each pointer optional), rows split at l_split into an "A" part (l < l_split,
+ *   video tokens) and a "B" part (text tokens of the joint sequence):
+ *     rowA = b * strideA + l ,  rowB = b * strideB + (l - l_split)       (strides in rows)
+ *     rawA_f32[rowA] / rawB_f32[rowB]   = y
+ *     nrmA_bf16[rowA] / nrmB_bf16[rowB] = bf16(y / ||y||_2)  ; nrmA_f32 / nrmB_f32 = y / ||y||_2
+ * in is fp32 (in_is_bf16 == 0) or bf16.  d % 128 == 0, d <= 1024.  eps = 1e-5 (torch default).
+ * Replaces: LayerNorm at model/tfm_model.py:35,:37 and model/tan_model.py:155,:167,:174,:206,:233;
+ * the positional add (:167,:199); torch.cat of video|text tokens (:201); torch.stack/permute of
+ * stage features (:176,:208); `x / x.norm(dim=-1)` (:116-117,:136-137). */
+typedef struct tan_ln_args {
+  const void* in;
+  int in_is_bf16;
+  int rows;
+  int d;
+  const float* gamma;
+  const float* beta;
+  const float* add;
+  int add_rows;
+  int L_in;
+  int L_out;
+  int l_off;
+  float* out_f32;
+  void* out_bf16;
+  int l_split;
+  int64_t strideA;
+  int64_t strideB;
+  float* rawA_f32;
+  float* rawB_f32;
+  void* nrmA_bf16;
+  void* nrmB_bf16;
+  float* nrmA_f32;
+  float* nrmB_f32;
+} tan_ln_args;
+TAN_API int tan_layernorm(const tan_ln_args* args, void* stream);
+
+/* ---- multi-head attention core ------------------------------------------------------------------ */
+
+/* out[b, i, h*64:(h+1)*64] = softmax_j(q_i . k_j / 8 + mask_j) @ v   for every clip b and head h.
+ *   q [B*Lq, *] bf16 (ldq), k/v [B*Lk, *] bf16 (ldk / ldv): head h occupies columns [64h, 64h+64)
+ *   relative to each base pointer (so a packed [M, 3d] in-projection output is passed as
+ *   q = qkv, k = qkv + d, v = qkv + 2d, ldq = ldk = ldv = 3d);
+ *   key_padding_mask [B, Lk] uint8 (1 = ignore key) or NULL; out [B*Lq, H*64] bf16 (ldo).
+ * head_dim is fixed at 64 (the reference hard-codes width 512 / 8 heads, model/tan_model.py:43-46;
+ * config 4 uses width 768 / 12 heads).  A row whose keys are all masked yields NaN, as
+ * torch.softmax over all -inf does in the reference.
+ * Replaces F.scaled_dot_product_attention + the [L,B,C]<->[B*H,L,hd] transposes reached from
+ * nn.MultiheadAttention at model/tfm_model.py:32 (self-attention, Lq == Lk) and :80
+ * (cross-attention of the unused decoder, Lq != Lk). */
+TAN_API int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                       const uint8_t* key_padding_mask, void* out, int64_t ldo, int B, int H, int Lq,
+                       int Lk, void* stream);
+
+/* ---- cosine-similarity matrix + MIL-NCE statistics ----------------------------------------------- */
+
+/* Geometry shared by the similarity / NCE entry points.
+ *   rows   r = (b * S + s) * T + t   for local clip b < B_loc, stage s < S, frame t < T
+ *   cols   c = b' * N + n            for GLOBAL clip b' and sentence n;  C = B_glob * N
+ *   z[r, c] = <vfeat[r], tfeat_s[c]> / 0.07                       (train/loss.py:65-67)
+ *   positive(r, c) <=> b_off + b == b' and col_valid[c] and start[c] <= t < end[c]
+ *                                                   (train/loss.py:26-41,:80-85)
+ * Sums use the fixed shift 1/0.07 (|cos| <= 1):  e = exp(z - 1/0.07). */
+typedef struct tan_sim_geom {
+  int B_loc;   /* local clips (rows) */
+  int S;       /* stages */
+  int T;       /* frames per clip */
+  int C;       /* global text columns = B_glob * N */
+  int N;       /* sentences per clip (padded) */
+  int d;       /* feature width */
+  int b_off;   /* global index of local clip 0 */
+} tan_sim_geom;
+
+/* Workspace (bytes) for tan_sim_nce_fwd partial sums. */
+TAN_API size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g);
+
+/* Fused similarity GEMM + NCE statistics.
+ *   vfeat [B_loc*S*T, d] bf16 L2-normalised video stage features (layout [B_loc, S, T, d]);
+ *   tfeat bf16 L2-normalised text features: [C, d] shared by all stages (tfeat_stage_stride == 0,
+ *         dual encoder, model/tan_model.py:118-119) or [S, C, d] (tfeat_stage_stride = C*d,
+ *         joint encoder, :138-139);
+ *   start/end [C] fp32 (padded sentences: start = T+100, end = -100, train/loss.py:32-39),
+ *   col_valid [C] uint8 (1 = real sentence, i.e. ~text_padding_mask);
+ *   logits_out: NULL (fused mode, the matrix never leaves the SM) or bf16 [B_loc*S*T, C] (ld = C),
+ *         written once = the reference's `logits_*` tensor [B,S,T,B,N] (cosines, NOT divided by 0.07);
+ *   row_sums [2, B_loc*S*T] fp32: sum_c e (valid columns) and sum_{c positive} e;
+ *   col_sums [2, S, C] fp32: sum_r e over the LOCAL rows (all rows, video padding is not applied
+ *         to rows, train/loss.py:241-254) and over positive rows.
+ * Replaces torch.einsum at model/tan_model.py:118-119,:138-139 and the logits passes of
+ * train/loss.py:65-67,:241-254,:261-271. */
+TAN_API int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfeat_stage_stride,
+                    const tan_sim_geom* g, const float* start, const float* end,
+                    const uint8_t* col_valid, void* logits_out, float* row_sums, float* col_sums,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same statistics from MATERIALISED logits (API-preserving mode: a caller hands get_loss a plain
+ * `logits_*` tensor).  logits [B_loc*S*T, C] bf16 (logits_is_f32 == 0) or fp32, unscaled cosines.
+ * HBM-bound: one coalesced pass, warp-shuffle row reductions, register column accumulators. */
+TAN_API int tan_nce_from_logits(const void* logits, int logits_is_f32, const tan_sim_geom* g,
+                        const float* start, const float* end, const uint8_t* col_valid,
+                        float* row_sums, float* col_sums, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* Loss reduction (train/loss.py:248-256): from row_sums [2, R] and (globally reduced) col_sums
+ * [2, S, C] accumulate
+ *   out[0] += sum over rows with a positive of log(all) - log(pos),  out[1] += their count,
+ *   out[2] += sum over valid columns with a positive of log(all) - log(pos), out[3] += their count.
+ * `out` [4] fp64 must be zeroed by the caller (fp64 so that the atomic accumulation order is
+ * invisible at fp32 resolution); rows and columns may be reduced by separate calls / ranks. */
+TAN_API int tan_nce_reduce(const float* row_sums, int64_t R, const float* col_sums, int64_t SC,
+                   int do_rows, int do_cols, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAN_B200_H_ */

@@ -1,0 +1,487 @@
+// Cosine-similarity matrix + MIL-NCE statistics.
+//
+//  * tan_sim_nce_fwd      fused: tcgen05 GEMM (umma_gemm.cuh) whose epilogue turns each 128 x BN
+//                         accumulator tile into exp-sums per row and per column (all / positive),
+//                         optionally storing the bf16 logits once.  In fused mode the
+//                         [B*T x B*N] x S matrix never reaches HBM.
+//  * tan_nce_from_logits  the same statistics from a materialised logits tensor: one coalesced
+//                         streaming pass (HBM-bound), warp-shuffle row reductions, register column
+//                         accumulators.
+//  * tan_nce_reduce       rows/columns -> the four scalars of train/loss.py:248-256.
+//
+// All sums use the fixed shift 1/0.07 (cosines are bounded by 1), so no running max is needed and
+// partial sums from different tiles / ranks add directly:  e = exp((cos - 1)/0.07) in (0, 1].
+#include "umma_gemm.cuh"
+
+namespace tanb {
+
+constexpr float kInvTemp = 1.0f / 0.07f;                       // train/loss.py:66
+constexpr float kExpScale = kInvTemp * 1.4426950408889634f;    // to the exp2 domain
+
+struct SimCommon {
+  tan_sim_geom g;
+  const float* start;
+  const float* end;
+  const uint8_t* col_valid;
+  int seg_tiles;     // row tiles per (clip, stage) segment = ceil(T / 128)
+  int m_tiles;       // B_loc * S * seg_tiles
+  int n_tiles;       // ceil(C / BN)
+  int64_t R;         // B_loc * S * T
+};
+
+// Transposing butterfly: on entry lane l holds v[j] = value(row l, column j); on exit lane l holds
+// the sum over the warp's 32 rows of column `l`.  31 shuffles.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float keep = upper ? v[j + half] : v[j];
+      const float send = upper ? v[j] : v[j + half];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+struct SimEpi {
+  // per-quarter column partials: [4 quarters][2 (all,pos)][BN]
+  static constexpr int kExtraSmem = 4 * 2 * BN * 4;
+  SimCommon c;
+  int64_t b_stage_rows;    // rows of B per stage in the B tensor map (0 for the dual encoder)
+  bf16* logits;            // optional [R, C]
+  float* row_part;         // [2][n_tiles][R]
+  float* col_part;         // [2][m_tiles][C]
+
+  __device__ __forceinline__ int num_tiles() const { return c.m_tiles * c.n_tiles; }
+  __device__ __forceinline__ TileCoord coord(int tile) const {
+    const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
+    const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
+    TileCoord tc;
+    tc.a_row = seg * c.g.T + i * kGemmBM;
+    tc.b_row = static_cast<int>((seg % c.g.S) * b_stage_rows) + tn * BN;
+    return tc;
+  }
+
+  __device__ __forceinline__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch) const {
+    const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
+    const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
+    const int t = i * kGemmBM + quarter * 32 + lane;          // frame index of this thread's row
+    const bool row_ok = t < c.g.T;
+    const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
+    const int bg = c.g.b_off + seg / c.g.S;                   // global clip of this row
+    const int pos_c0 = bg * c.g.N, pos_c1 = pos_c0 + c.g.N;   // the only columns that can be positive
+    const float tf = static_cast<float>(t);
+    const int n0 = tn * BN;
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* scol = reinterpret_cast<float*>(scratch) + quarter * 2 * BN;
+    float row_all = 0.f, row_pos = 0.f;
+    const bool vec_store = (c.g.C % 8) == 0;
+
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      const int col0 = n0 + ch * 32;
+      if (col0 >= c.g.C) {                                    // warp-uniform: nothing but zeros left
+        scol[ch * 32 + lane] = 0.f;
+        scol[BN + ch * 32 + lane] = 0.f;
+        continue;
+      }
+      uint32_t raw[32];
+      tmem_ld_32x32(taddr + ch * 32, raw);
+      tmem_ld_wait();
+      // lane j looks up column col0 + j once; shuffled to everyone below
+      const int mycol = col0 + lane;
+      const bool my_ok = mycol < c.g.C && c.col_valid[mycol] != 0;
+      const uint32_t okmask = __ballot_sync(0xffffffffu, my_ok);
+      const bool chunk_has_pos = col0 < pos_c1 && col0 + 32 > pos_c0;   // warp-uniform
+      float my_start = 0.f, my_end = 0.f;
+      if (chunk_has_pos && my_ok && mycol >= pos_c0 && mycol < pos_c1) {
+        my_start = c.start[mycol];
+        my_end = c.end[mycol];                                           // else start >= end: never positive
+      }
+      if (logits != nullptr && row_ok) {
+        bf16* dst = logits + r * c.g.C + col0;
+        if (vec_store && col0 + 32 <= c.g.C) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(raw[8 * j + 0]), __uint_as_float(raw[8 * j + 1]));
+            u.y = pack_bf16x2(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3]));
+            u.z = pack_bf16x2(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5]));
+            u.w = pack_bf16x2(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7]));
+            reinterpret_cast<uint4*>(dst)[j] = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < c.g.C) dst[j] = __float2bfloat16_rn(__uint_as_float(raw[j]));
+        }
+      }
+      float e[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = fast_exp2(fmaf(__uint_as_float(raw[j]), kExpScale, -kExpScale));
+        e[j] = (row_ok && ((okmask >> j) & 1u)) ? x : 0.f;
+        row_all += e[j];
+      }
+      float pe[32];
+      if (chunk_has_pos) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __shfl_sync(0xffffffffu, my_start, j);
+          const float en = __shfl_sync(0xffffffffu, my_end, j);
+          pe[j] = (s <= tf && tf < en) ? e[j] : 0.f;
+          row_pos += pe[j];
+        }
+      }
+      const float call = warp_column_sums(e, lane);
+      scol[ch * 32 + lane] = call;
+      float cpos = 0.f;
+      if (chunk_has_pos) cpos = warp_column_sums(pe, lane);
+      scol[BN + ch * 32 + lane] = cpos;
+    }
+    if (row_ok) {
+      row_part[(static_cast<int64_t>(0) * c.n_tiles + tn) * c.R + r] = row_all;
+      row_part[(static_cast<int64_t>(1) * c.n_tiles + tn) * c.R + r] = row_pos;
+    }
+    // combine the four quarters in a fixed order (deterministic) and publish this tile's column partials
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const float* s0 = reinterpret_cast<const float*>(scratch);
+    const int tid = quarter * 32 + lane;
+    for (int j = tid; j < 2 * BN; j += kEpiThreads) {
+      const int which = j / BN, cj = j % BN;
+      const int col = n0 + cj;
+      if (col < c.g.C) {
+        const float sum = ((s0[0 * 2 * BN + j] + s0[1 * 2 * BN + j]) + s0[2 * 2 * BN + j]) + s0[3 * 2 * BN + j];
+        col_part[(static_cast<int64_t>(which) * c.m_tiles + tm) * c.g.C + col] = sum;
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch is reused by the next tile
+  }
+};
+
+// row_sums[w][r] = sum_tn row_part[w][tn][r];  col_sums[w][s][c] = sum over the m-tiles of stage s.
+__global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part,
+                                           SimCommon c, float* __restrict__ row_sums, float* __restrict__ col_sums) {
+  const int64_t nrow = 2 * c.R;
+  const int64_t ncol = 2ll * c.g.S * c.g.C;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nrow + ncol; i += stride) {
+    if (i < nrow) {
+      const int64_t w = i / c.R, r = i % c.R;
+      float s = 0.f;
+      for (int tn = 0; tn < c.n_tiles; ++tn) s += row_part[(w * c.n_tiles + tn) * c.R + r];
+      row_sums[i] = s;
+    } else {
+      const int64_t k = i - nrow;
+      const int64_t w = k / (static_cast<int64_t>(c.g.S) * c.g.C);
+      const int64_t rem = k % (static_cast<int64_t>(c.g.S) * c.g.C);
+      const int s_idx = static_cast<int>(rem / c.g.C), col = static_cast<int>(rem % c.g.C);
+      float s = 0.f;
+      for (int b = 0; b < c.g.B_loc; ++b) {
+        const int seg = b * c.g.S + s_idx;
+        for (int t = 0; t < c.seg_tiles; ++t)
+          s += col_part[(w * c.m_tiles + (seg * c.seg_tiles + t)) * c.g.C + col];
+      }
+      col_sums[k] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Statistics from materialised logits.
+// CTA = 8 warps; a CTA owns a (segment, 256-column slab) and walks the segment's T rows, warp w
+// taking rows w, w+8, ...  Each lane owns 8 consecutive columns (one 16-byte load of bf16, two of
+// fp32), so a warp reads 512 contiguous bytes per row; column sums live in registers for the whole
+// walk; row sums need one shuffle reduction per row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNceCols = 256;
+constexpr int kNceWarps = 8;
+
+template <bool F32>
+__global__ void __launch_bounds__(kNceWarps * 32)
+nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, float* __restrict__ row_part,
+                       float* __restrict__ col_sums_part) {
+  __shared__ float scol[kNceWarps][2][kNceCols];
+  const int slab = blockIdx.x;                 // column slab
+  const int seg = blockIdx.y;                  // (clip, stage)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = slab * kNceCols + lane * 8;
+  const int bg = c.g.b_off + seg / c.g.S;
+  const int pos_c0 = bg * c.g.N, pos_c1 = pos_c0 + c.g.N;
+  const bool aligned = (c.g.C % 8) == 0;
+
+  bool ok[8];
+  float st[8], en[8];
+  bool any_pos_col = false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = col0 + j;
+    ok[j] = col < c.g.C && c.col_valid[col] != 0;
+    const bool pc = ok[j] && col >= pos_c0 && col < pos_c1;
+    st[j] = pc ? c.start[col] : 1.f;
+    en[j] = pc ? c.end[col] : 0.f;
+    any_pos_col |= pc;
+  }
+  float call[8], cpos[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { call[j] = 0.f; cpos[j] = 0.f; }
+
+  for (int t = warp; t < c.g.T; t += kNceWarps) {
+    const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
+    float x[8];
+    if (aligned && col0 + 8 <= c.g.C) {
+      if (F32) {
+        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(logits) + r * c.g.C + col0);
+        const float4 a = p[0], b = p[1];
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(logits) + r * c.g.C + col0);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = cc.x; x[5] = cc.y; x[6] = d.x; x[7] = d.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = col0 + j;
+        x[j] = 0.f;
+        if (col < c.g.C)
+          x[j] = F32 ? static_cast<const float*>(logits)[r * c.g.C + col]
+                     : __bfloat162float(static_cast<const bf16*>(logits)[r * c.g.C + col]);
+      }
+    }
+    const float tf = static_cast<float>(t);
+    float ra = 0.f, rp = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = ok[j] ? fast_exp2(fmaf(x[j], kExpScale, -kExpScale)) : 0.f;
+      call[j] += e;
+      ra += e;
+      if (any_pos_col) {
+        const float pe = (st[j] <= tf && tf < en[j]) ? e : 0.f;
+        cpos[j] += pe;
+        rp += pe;
+      }
+    }
+    ra = warp_sum(ra);
+    rp = warp_sum(rp);
+    if (lane == 0) {
+      row_part[(static_cast<int64_t>(0) * gridDim.x + slab) * c.R + r] = ra;
+      row_part[(static_cast<int64_t>(1) * gridDim.x + slab) * c.R + r] = rp;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    scol[warp][0][lane * 8 + j] = call[j];
+    scol[warp][1][lane * 8 + j] = cpos[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * kNceCols; j += blockDim.x) {
+    const int which = j / kNceCols, cj = j % kNceCols;
+    const int col = slab * kNceCols + cj;
+    if (col < c.g.C) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kNceWarps; ++w) s += scol[w][which][cj];
+      // one partial per segment: [2][B_loc*S][C]
+      col_sums_part[(static_cast<int64_t>(which) * gridDim.y + seg) * c.g.C + col] = s;
+    }
+  }
+}
+
+__global__ void nce_reduce_kernel(const float* __restrict__ row_sums, int64_t R, const float* __restrict__ col_sums,
+                                  int64_t SC, int do_rows, int do_cols, double* __restrict__ out) {
+  // fp64 accumulation: the cross-block atomic order then only perturbs bits far below fp32 epsilon
+  double acc[4] = {0., 0., 0., 0.};
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (do_rows) {
+    for (int64_t i = i0; i < R; i += stride) {
+      const float all = row_sums[i], pos = row_sums[R + i];
+      if (pos > 0.f) { acc[0] += static_cast<double>(logf(all) - logf(pos)); acc[1] += 1.; }
+    }
+  }
+  if (do_cols) {
+    for (int64_t i = i0; i < SC; i += stride) {
+      const float all = col_sums[i], pos = col_sums[SC + i];
+      if (pos > 0.f) { acc[2] += static_cast<double>(logf(all) - logf(pos)); acc[3] += 1.; }
+    }
+  }
+  __shared__ double sred[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sred[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double v = lane < (blockDim.x >> 5) ? sred[k][lane] : 0.;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && v != 0.) atomicAdd(out + k, v);
+    }
+  }
+}
+
+static int fill_common(SimCommon* c, const tan_sim_geom* g, const float* start, const float* end,
+                       const uint8_t* col_valid, int bn) {
+  if (g == nullptr || start == nullptr || end == nullptr || col_valid == nullptr)
+    return set_error(TAN_ERR_ARG, "sim/nce: null geometry or mask pointer");
+  if (g->B_loc <= 0 || g->S <= 0 || g->T <= 0 || g->C <= 0 || g->N <= 0 || g->d <= 0 || g->b_off < 0 ||
+      g->C % g->N != 0)
+    return set_error(TAN_ERR_SHAPE, "sim/nce: bad geometry B_loc=%d S=%d T=%d C=%d N=%d d=%d", g->B_loc, g->S, g->T,
+                     g->C, g->N, g->d);
+  c->g = *g;
+  c->start = start;
+  c->end = end;
+  c->col_valid = col_valid;
+  c->seg_tiles = (g->T + kGemmBM - 1) / kGemmBM;
+  c->m_tiles = g->B_loc * g->S * c->seg_tiles;
+  c->n_tiles = (g->C + bn - 1) / bn;
+  c->R = static_cast<int64_t>(g->B_loc) * g->S * g->T;
+  return TAN_OK;
+}
+
+static int pick_bn(const tan_sim_geom* g) {
+  if (g->C > 128) return 256;
+  if (g->C > 64) return 128;
+  return 64;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+template <int BN>
+static int launch_sim(const CUtensorMap& tmA, const CUtensorMap& tmB, SimEpi<BN> epi, int d, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = umma_gemm_kernel<BN, SimEpi<BN>>;
+  constexpr int smem = Cfg::kSmemBytes + SimEpi<BN>::kExtraSmem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int tiles = epi.c.m_tiles * epi.c.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, epi, d / kGemmBK);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+}  // namespace tanb
+
+using namespace tanb;
+
+extern "C" size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g) {
+  if (g == nullptr || g->B_loc <= 0 || g->S <= 0 || g->T <= 0 || g->C <= 0) return 0;
+  // sized for the smallest tile width either producer may pick (64 for the GEMM, 256-col slabs for
+  // the streaming kernel) so one query covers both entry points
+  const int64_t R = static_cast<int64_t>(g->B_loc) * g->S * g->T;
+  const int64_t n_tiles = (g->C + 63) / 64;
+  const int64_t seg_tiles = (g->T + kGemmBM - 1) / kGemmBM;
+  const int64_t m_tiles = static_cast<int64_t>(g->B_loc) * g->S * seg_tiles;
+  return align256(2 * n_tiles * R * 4) + align256(2 * m_tiles * g->C * 4);
+}
+
+extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfeat_stage_stride,
+                               const tan_sim_geom* g, const float* start, const float* end,
+                               const uint8_t* col_valid, void* logits_out, float* row_sums, float* col_sums,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (vfeat == nullptr || tfeat == nullptr || row_sums == nullptr || col_sums == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_sim_nce_fwd: null pointer");
+  if (g == nullptr) return set_error(TAN_ERR_ARG, "tan_sim_nce_fwd: null geometry");
+  const int bn = pick_bn(g);
+  SimCommon c;
+  TAN_CHECK(fill_common(&c, g, start, end, col_valid, bn));
+  if (g->d % kGemmBK != 0) return set_error(TAN_ERR_SHAPE, "tan_sim_nce_fwd: d %% 64 != 0 (d=%d)", g->d);
+  if (tfeat_stage_stride != 0 && tfeat_stage_stride != static_cast<int64_t>(g->C) * g->d)
+    return set_error(TAN_ERR_SHAPE, "tan_sim_nce_fwd: tfeat_stage_stride must be 0 or C*d");
+  if (workspace == nullptr || workspace_bytes < tan_sim_nce_workspace_bytes(g))
+    return set_error(TAN_ERR_WORKSPACE, "tan_sim_nce_fwd: workspace too small (%zu < %zu)", workspace_bytes,
+                     tan_sim_nce_workspace_bytes(g));
+  float* row_part = static_cast<float*>(workspace);
+  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                             align256(2 * static_cast<size_t>(c.n_tiles) * c.R * 4));
+  const int64_t b_rows = tfeat_stage_stride == 0 ? g->C : static_cast<int64_t>(g->S) * g->C;
+  CUtensorMap tmA, tmB;
+  TAN_CHECK(make_tmap_2d_bf16(&tmA, vfeat, c.R, g->d, g->d, kGemmBM, kGemmBK));
+  TAN_CHECK(make_tmap_2d_bf16(&tmB, tfeat, b_rows, g->d, g->d, bn, kGemmBK));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TAN_LAUNCH_SIM(BN_)                                                          \
+  {                                                                                  \
+    SimEpi<BN_> e;                                                                   \
+    e.c = c;                                                                         \
+    e.b_stage_rows = tfeat_stage_stride == 0 ? 0 : g->C;                             \
+    e.logits = static_cast<bf16*>(logits_out);                                       \
+    e.row_part = row_part;                                                           \
+    e.col_part = col_part;                                                           \
+    TAN_CHECK(launch_sim<BN_>(tmA, tmB, e, g->d, st));                               \
+  }
+  if (bn == 256) TAN_LAUNCH_SIM(256)
+  else if (bn == 128) TAN_LAUNCH_SIM(128)
+  else TAN_LAUNCH_SIM(64)
+#undef TAN_LAUNCH_SIM
+  const int64_t total = 2 * c.R + 2ll * g->S * g->C;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  sim_reduce_partials_kernel<<<blocks, 256, 0, st>>>(row_part, col_part, c, row_sums, col_sums);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const tan_sim_geom* g,
+                                   const float* start, const float* end, const uint8_t* col_valid,
+                                   float* row_sums, float* col_sums, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (logits == nullptr || row_sums == nullptr || col_sums == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_nce_from_logits: null pointer");
+  if (g == nullptr) return set_error(TAN_ERR_ARG, "tan_nce_from_logits: null geometry");
+  SimCommon c;
+  TAN_CHECK(fill_common(&c, g, start, end, col_valid, kNceCols));
+  if (workspace == nullptr || workspace_bytes < tan_sim_nce_workspace_bytes(g))
+    return set_error(TAN_ERR_WORKSPACE, "tan_nce_from_logits: workspace too small (%zu < %zu)", workspace_bytes,
+                     tan_sim_nce_workspace_bytes(g));
+  // reuse the partial layout of the fused kernel with one "m tile" per segment
+  c.seg_tiles = 1;
+  c.m_tiles = g->B_loc * g->S;
+  float* row_part = static_cast<float*>(workspace);
+  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                             align256(2 * static_cast<size_t>(c.n_tiles) * c.R * 4));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->B_loc * g->S > 65535) return set_error(TAN_ERR_SHAPE, "tan_nce_from_logits: B_loc*S > 65535");
+  dim3 grid(c.n_tiles, g->B_loc * g->S);
+  if (logits_is_f32)
+    nce_from_logits_kernel<true><<<grid, kNceWarps * 32, 0, st>>>(logits, c, row_part, col_part);
+  else
+    nce_from_logits_kernel<false><<<grid, kNceWarps * 32, 0, st>>>(logits, c, row_part, col_part);
+  TAN_CUDA(cudaGetLastError());
+  const int64_t total = 2 * c.R + 2ll * g->S * g->C;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  sim_reduce_partials_kernel<<<blocks, 256, 0, st>>>(row_part, col_part, c, row_sums, col_sums);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_nce_reduce(const float* row_sums, int64_t R, const float* col_sums, int64_t SC, int do_rows,
+                              int do_cols, double* out, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (out == nullptr || (do_rows && row_sums == nullptr) || (do_cols && col_sums == nullptr))
+    return set_error(TAN_ERR_ARG, "tan_nce_reduce: null pointer");
+  const int64_t n = (do_rows ? R : 0) > (do_cols ? SC : 0) ? R : SC;
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  nce_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, R, col_sums, SC, do_rows,
+                                                                            do_cols, out);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}

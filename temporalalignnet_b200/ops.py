@@ -1,0 +1,127 @@
+"""Tensor-level wrappers over the C ABI (include/tan_b200.h).
+
+torch is used here only for device memory and the current CUDA stream; every arithmetic step is a
+kernel of libtan_b200.so.  All functions launch asynchronously on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import LnArgs, SimGeom, check, lib
+
+_launches = 0          # kernels launched through this module (bench.py's `gpu_launches` claim)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise _lib.TanError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} {t.device} "
+                            f"contiguous={t.is_contiguous()}")
+
+
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 -> bf16 (tan_cast_f32_to_bf16)."""
+    global _launches
+    _need(x, torch.float32, "cast_bf16.in")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().tan_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "tan_cast_f32_to_bf16")
+    _launches += 1
+    return out
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+           out_bf16: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE) -> None:
+    """out = act(a @ w.T + bias) [+ residual]  (tan_linear_bf16).  a [M,K] bf16 (row pitch may exceed
+    K), w [N,K] bf16; outputs 2-D with arbitrary row pitch."""
+    global _launches
+    M, K = a.shape
+    N = w.shape[0]
+    check(lib().tan_linear_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+        _ptr(residual), residual.stride(0) if residual is not None else 0,
+        _ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+        _ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
+        M, N, K, act, _stream()), "tan_linear_bf16")
+    _launches += 1
+
+
+def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=None, add_rows: int = 0,
+              L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0,
+              out_f32=None, out_bf16=None, l_split: int = 0, strideA: int = 0, strideB: int = 0,
+              rawA=None, rawB=None, nrmA_bf16=None, nrmB_bf16=None, nrmA_f32=None, nrmB_f32=None) -> None:
+    """tan_layernorm; pointer-valued keyword arguments are tensors whose data_ptr() already points at
+    the first destination row (callers pass views)."""
+    global _launches
+    L_in = rows if L_in is None else L_in
+    L_out = L_in if L_out is None else L_out
+    a = LnArgs(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, d, _ptr(gamma), _ptr(beta), _ptr(add), add_rows,
+               L_in, L_out, l_off, _ptr(out_f32), _ptr(out_bf16), l_split, strideA, strideB,
+               _ptr(rawA), _ptr(rawB), _ptr(nrmA_bf16), _ptr(nrmB_bf16), _ptr(nrmA_f32), _ptr(nrmB_f32))
+    check(lib().tan_layernorm(C.byref(a), _stream()), "tan_layernorm")
+    _launches += 1
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kpm_u8: Optional[torch.Tensor],
+              out: torch.Tensor, B: int, H: int, Lq: int, Lk: int) -> None:
+    """tan_attention_bf16.  q/k/v/out are 2-D (possibly column-sliced) bf16 views [B*L, H*64]."""
+    global _launches
+    check(lib().tan_attention_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                   _ptr(kpm_u8), out.data_ptr(), out.stride(0), B, H, Lq, Lk, _stream()),
+          "tan_attention_bf16")
+    _launches += 1
+
+
+def sim_geom(B_loc, S, T, C_, N, d, b_off=0) -> SimGeom:
+    return SimGeom(B_loc, S, T, C_, N, d, b_off)
+
+
+def sim_workspace_bytes(g: SimGeom) -> int:
+    return int(lib().tan_sim_nce_workspace_bytes(C.byref(g)))
+
+
+def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride: int, g: SimGeom, start, end, col_valid, logits_out,
+                row_sums, col_sums, workspace) -> None:
+    global _launches
+    check(lib().tan_sim_nce_fwd(vfeat.data_ptr(), tfeat.data_ptr(), tfeat_stage_stride, C.byref(g), start.data_ptr(),
+                                end.data_ptr(), col_valid.data_ptr(), _ptr(logits_out), row_sums.data_ptr(),
+                                col_sums.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                _stream()), "tan_sim_nce_fwd")
+    _launches += 2
+
+
+def nce_from_logits(logits, g: SimGeom, start, end, col_valid, row_sums, col_sums, workspace) -> None:
+    global _launches
+    is_f32 = int(logits.dtype == torch.float32)
+    if not is_f32 and logits.dtype != torch.bfloat16:
+        raise _lib.TanError(f"nce_from_logits: logits must be fp32 or bf16, got {logits.dtype}")
+    check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), start.data_ptr(), end.data_ptr(),
+                                    col_valid.data_ptr(), row_sums.data_ptr(), col_sums.data_ptr(),
+                                    workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()),
+          "tan_nce_from_logits")
+    _launches += 2
+
+
+def nce_reduce(row_sums, col_sums, out4_f64, do_rows=True, do_cols=True) -> None:
+    global _launches
+    R = row_sums.numel() // 2 if row_sums is not None else 0
+    SC = col_sums.numel() // 2 if col_sums is not None else 0
+    check(lib().tan_nce_reduce(_ptr(row_sums), R, _ptr(col_sums), SC, int(do_rows), int(do_cols),
+                               out4_f64.data_ptr(), _stream()), "tan_nce_reduce")
+    _launches += 1
