@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- clips/sec of the TAN hot path (forward + MIL-NCE loss) on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...       # the reference's CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json metric / configs[2] per-GPU shape): E6D6, T=256 frames, d=512, 32 clips per
+GPU (weak scaling: global batch = 32 * N, contrastive negatives span the global batch), N=32
+sentences per clip, synthetic features (seed 888), reference-init weights.  One "step" = one
+`TemporalAligner.forward` + `get_loss` (`--model init`) over the batch; the reference's backward /
+optimizer are not part of this metric (forward+loss is what §8 row (a) covers this round).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
+`e2e` = the same through the public API from pinned host memory (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+E_LAYERS, D_LAYERS, T_FRAMES, WIDTH, B_PER_GPU, N_TEXT, VIDEO_DIM = 6, 6, 256, 512, 32, 32, 1024
+CPU_SAMPLE_CLIPS = 16
+METRIC = "clips/sec (forward + MIL-NCE loss; E6D6, T=256, d=512, 32 clips/GPU, global negatives)"
+
+
+def workload_config(n_gpus):
+    return {"workload": f"BASELINE configs[2] per-GPU shape: E6D6 T={T_FRAMES} d={WIDTH} B_loc={B_PER_GPU} "
+                        f"N={N_TEXT} D_in={VIDEO_DIM}, global batch {B_PER_GPU * n_gpus}",
+            "step": "TemporalAligner.forward + get_loss(model=init), fused similarity+NCE (no logits in HBM)",
+            "global_batch": B_PER_GPU * n_gpus, "seq_len": T_FRAMES,
+            "parallelism": f"dp{n_gpus} (video batch sharded; text features all-gathered)" if n_gpus > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write), each step timed by its own CUDA event pair"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_clips_per_sec(steps, warmup, clips=CPU_SAMPLE_CLIPS):
+    """Times oracle/tan_oracle.py (fp32 torch-CPU restatement of model/tan_model.py forward +
+    train/loss.py get_loss; the reference itself is Python-on-torch and /root/reference does not
+    exist on the GPU box) on a bounded sample of the workload: `clips` clips of the same shape."""
+    import torch
+
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.make_state_dict(E_LAYERS, D_LAYERS, perturb=False)
+    batch = synth.make_batch(clips, T_FRAMES, N_TEXT)
+    orc = O.TanOracle(sd, E_LAYERS, D_LAYERS)
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+
+    def step():
+        with torch.no_grad():
+            out = orc.forward(video, text, batch["video_padding_mask"], batch["text_padding_mask"])
+            return float(O.get_loss_init(out["logits_dual"], out["logits_joint"], batch["start"], batch["end"],
+                                         batch["text_padding_mask"])["loss"])
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return {"value": clips / (sum(times) / len(times)), "best": clips / min(times), "cores": cores,
+            "sample": f"{clips} clips (E6D6, T={T_FRAMES}, N={N_TEXT}; negatives span the {clips}-clip sample), "
+                      f"fp32 torch-CPU oracle port, {warmup} warm-up + mean of {steps} steps",
+            "ms_per_step": 1e3 * sum(times) / len(times)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_clips_per_sec(args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": round(r["value"], 3), "unit": "clips/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": round(r["value"], 3), "unit": "clips/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from temporalalignnet_b200 import ops
+    from temporalalignnet_b200.runner import TanStepRunner
+
+    steps, warmup = args.steps, max(args.warmup, 3)
+    runner = TanStepRunner(E_LAYERS, D_LAYERS, B_PER_GPU, T_FRAMES, N_TEXT, WIDTH, VIDEO_DIM, device=f"cuda:{local}",
+                           rank=rank, world_size=world, use_graph=not args.no_graph)
+    loss0 = runner.warmup(warmup)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident steps ------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    n0 = ops.launches()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        loss_t = runner.step_resident()
+        ev[i][1].record()
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+    value = B_PER_GPU * world / (ms_per_step * 1e-3)
+    launches_per_step = runner.launches_per_step
+    loss_val = float(loss_t)
+
+    # ---- timed region 2: end to end through the public API, from pinned host memory ---------------
+    for _ in range(2):
+        runner.step_api()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss_api = runner.step_api()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = B_PER_GPU * world * steps / e2e_s
+
+    # ---- roofline pass: per-kernel CUDA events on the launching stream, same steps, eager launches
+    with ops.profile() as prof:
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            runner._step_kernels()
+        barrier()
+        agg = {}
+        for name, work, e0, e1 in prof:
+            a = agg.setdefault(name, [0.0, 0.0, 0])
+            a[0] += work; a[1] += e0.elapsed_time(e1); a[2] += 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
+        "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    lin = agg.get("linear", [0.0, 1.0, 1])
+    lin_tf = lin[0] / (lin[1] * 1e-3) / 1e12
+    kernel_ms = {k: round(v[1] / steps, 4) for k, v in agg.items()}
+    roofline = {"kernel": "umma_gemm_kernel<LinearEpi> (tan_linear_bf16: QKV/out/MLP/pre projections)",
+                "bound": "tensor", "achieved": round(lin_tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": round(lin_tf / tf_peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": lin[2] // steps, "avg_launch_us": round(1e3 * lin[1] / max(lin[2], 1), 2),
+                "share_of_step": round(lin[1] / max(sum(v[1] for v in agg.values()), 1e-9), 3)}
+    extra = {}
+    if "sim_nce_fwd" in agg:
+        s = agg["sim_nce_fwd"]
+        extra["roofline_sim"] = {"kernel": "umma_gemm_kernel<SimEpi> (tan_sim_nce_fwd, fused mode)", "bound": "tensor",
+                                 "achieved": round(s[0] / (s[1] * 1e-3) / 1e12, 1), "peak": tf_peak, "unit": "TFLOP/s",
+                                 "frac": round(s[0] / (s[1] * 1e-3) / 1e12 / tf_peak, 4)}
+    fl = runner.flops_per_clip()
+    extra["whole_step_tensor_frac"] = round(fl["total"] * B_PER_GPU / (ms_per_step * 1e-3) / 1e12 / tf_peak, 4)
+    extra["kernel_ms_per_step"] = kernel_ms
+
+    # ---- HBM-bound contrastive pass on materialised logits (API-preserving mode), rank 0 only --------
+    if rank == 0 and not args.skip_hbm:
+        extra["roofline_nce_hbm"] = hbm_nce_roofline(runner, peaks, flush)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        r = cpu_reference_clips_per_sec(3, 1)
+        cpu = {"value": round(r["best"], 3), "unit": "clips/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"].replace("mean of 3", "best of 3")}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "clips/s", "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+                "loss": round(loss_val, 6), "loss_api": round(loss_api, 6), "cuda_graph": runner._graph is not None,
+                "e2e": {"value": round(e2e_value, 1), "unit": "clips/s", "h2d_bytes_per_step": runner.h2d_bytes,
+                        "d2h_bytes_per_step": runner.d2h_bytes},
+                "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def hbm_nce_roofline(runner, peaks, flush):
+    """tan_nce_from_logits on the materialised bf16 logits of this workload: algorithmic bytes =
+    the logits read once; measured with CUDA events, L2 flushed."""
+    import torch
+
+    from temporalalignnet_b200 import loss as loss_mod
+    from temporalalignnet_b200 import ops
+    out = runner.model(runner.d_video, runner.d_text, video_padding_mask=runner.d_vpm, lang_padding_mask=runner.d_tpm)
+    lg = out["logits_joint"]
+    if runner.shard:
+        return None
+    dense = lg.materialize()
+    B, S, T, B2, N = dense.shape
+    g = ops.sim_geom(B, S, T, B2 * N, N, 1, 0)
+    rs = torch.empty(2, B * S * T, dtype=torch.float32, device=dense.device)
+    cs = torch.empty(2, S, B2 * N, dtype=torch.float32, device=dense.device)
+    ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dense.device)
+    nce = runner.nce
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.nce_from_logits(dense, g, nce.start, nce.end, nce.col_valid, rs, cs, ws)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    nbytes = dense.numel() * 2
+    hbm = float(peaks.get("hbm_gbs", 6650.0)) if peaks else 6650.0
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "nce_from_logits_kernel<bf16> + partial reduce (tan_nce_from_logits)", "bound": "hbm",
+            "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(gbs / hbm, 4), "traffic": None,
+            "bytes": nbytes, "ms": round(ms, 4)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-hbm", action="store_true", help="skip the materialised-logits HBM roofline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

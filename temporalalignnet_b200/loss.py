@@ -94,15 +94,48 @@ def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, 
         return NceInputs(start, end, valid, N, 0, B)
     W, rank = dist.get_world_size(), dist.get_rank()
     packed = torch.stack((start, end, valid.float()))                       # [3, B*N]
-    gathered = torch.empty(W, 3, B * N, dtype=torch.float32, device=device)
+    gathered = torch.empty(W * 3, B * N, dtype=torch.float32, device=device)     # concat along dim 0
     dist.all_gather_into_tensor(gathered, packed)
-    g = gathered.permute(1, 0, 2).reshape(3, W * B * N).contiguous()
+    g = gathered.view(W, 3, B * N).permute(1, 0, 2).reshape(3, W * B * N).contiguous()
     return NceInputs(g[0].contiguous(), g[1].contiguous(), g[2].to(torch.uint8).contiguous(), N, rank * B, W * B)
 
 
 def nce_stats_to_loss(out4: torch.Tensor) -> torch.Tensor:
     """(sum_v, n_v, sum_t, n_t) fp64 -> loss_x = (mean v + mean t) / 2 (train/loss.py:256) as fp32."""
     return ((out4[0] / out4[1] + out4[2] / out4[3]) * 0.5).float()
+
+
+def gather_text_features(tfeat: torch.Tensor, shared_text: bool, dist) -> torch.Tensor:
+    """The one exchange step of the path: every rank needs every clip's L2-normalised
+    text features.  [B_loc*N, d] -> [B*N, d] (dual) or [S, B_loc*N, d] -> [S, B*N, d] (joint), rank-major
+    so that global column c = (rank*B_loc + b)*N + n."""
+    W = dist.get_world_size()
+    d = tfeat.shape[-1]
+    if shared_text:
+        full = torch.empty(W * tfeat.shape[0], d, dtype=tfeat.dtype, device=tfeat.device)
+        dist.all_gather_into_tensor(full, tfeat.contiguous())
+        return full
+    S = tfeat.shape[0]
+    g = torch.empty(W * S, tfeat.shape[1], d, dtype=tfeat.dtype, device=tfeat.device)   # concat along dim 0
+    dist.all_gather_into_tensor(g, tfeat.contiguous())
+    return g.view(W, S, tfeat.shape[1], d).permute(1, 0, 2, 3).reshape(S, W * tfeat.shape[1], d).contiguous()
+
+
+def finish_loss(row_sums: torch.Tensor, col_sums: torch.Tensor, dist, reduce_fn=None) -> torch.Tensor:
+    """Exp-sums -> loss_x.  row_sums [2, R_local], col_sums [2, S, C] (partial over the local rows).
+    Distributed: column sums add across ranks (fixed-shift exp sums); row terms are reduced locally and
+    their (sum, count) all-reduced, so every rank returns the global-batch loss."""
+    reduce_fn = ops.nce_reduce if reduce_fn is None else reduce_fn
+    out4 = torch.zeros(4, dtype=torch.float64, device=row_sums.device)
+    if dist is None:
+        reduce_fn(row_sums, col_sums, out4)
+    else:
+        dist.all_reduce(col_sums)
+        reduce_fn(row_sums, col_sums, out4)             # cols now global and identical on every rank
+        rows = out4[:2].clone()
+        dist.all_reduce(rows)
+        out4 = torch.cat((rows, out4[2:]))
+    return nce_stats_to_loss(out4)
 
 
 def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
@@ -113,16 +146,7 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
         B, S, T, d = vfeat.shape
         dev = vfeat.device
         if dist is not None:
-            # the one exchange step of the path: every rank needs every clip's text features
-            W = dist.get_world_size()
-            if logits.shared_text:
-                full = torch.empty(W * tfeat.shape[0], d, dtype=tfeat.dtype, device=dev)
-                dist.all_gather_into_tensor(full, tfeat.contiguous())
-            else:
-                g = torch.empty(W, S, tfeat.shape[1], d, dtype=tfeat.dtype, device=dev)
-                dist.all_gather_into_tensor(g, tfeat.contiguous())
-                full = g.permute(1, 0, 2, 3).reshape(S, W * tfeat.shape[1], d).contiguous()
-            tfeat = full
+            tfeat = gather_text_features(tfeat, logits.shared_text, dist)
         C = tfeat.shape[-2]
         g = ops.sim_geom(B, S, T, C, nce.N, d, nce.b_off)
         row_sums = torch.empty(2, B * S * T, dtype=torch.float32, device=dev)
@@ -147,16 +171,7 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
         col_sums = torch.empty(2, S, C, dtype=torch.float32, device=dev)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
         ops.nce_from_logits(x, g, nce.start, nce.end, nce.col_valid, row_sums, col_sums, ws)
-    out4 = torch.zeros(4, dtype=torch.float64, device=dev)
-    if dist is None:
-        ops.nce_reduce(row_sums, col_sums, out4)
-    else:
-        dist.all_reduce(col_sums)                       # partial column sums add (fixed-shift exp sums)
-        ops.nce_reduce(row_sums, col_sums, out4)        # cols now global and identical on every rank
-        rows = out4[:2].clone()
-        dist.all_reduce(rows)                           # row terms: global sum and count
-        out4 = torch.cat((rows, out4[2:]))
-    return nce_stats_to_loss(out4)
+    return finish_loss(row_sums, col_sums, dist)
 
 
 def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding_mask, logits, args,

@@ -14,6 +14,38 @@ from . import _lib
 from ._lib import LnArgs, SimGeom, check, lib
 
 _launches = 0          # kernels launched through this module (bench.py's `gpu_launches` claim)
+_prof = None           # when a list: (kernel, work, start_event, end_event) per call (bench.py roofline pass)
+
+
+class profile:
+    """Context manager: bracket every C-ABI call with CUDA events on the launching stream."""
+
+    def __enter__(self):
+        global _prof
+        _prof = []
+        return _prof
+
+    def __exit__(self, *a):
+        global _prof
+        _prof = None
+
+
+class _timed:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name, work):
+        self.name, self.work, self.e0 = name, work, None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.name, self.work, self.e0, e1))
 
 
 def launches() -> int:
@@ -53,12 +85,13 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     global _launches
     M, K = a.shape
     N = w.shape[0]
-    check(lib().tan_linear_bf16(
-        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
-        _ptr(residual), residual.stride(0) if residual is not None else 0,
-        _ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-        _ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
-        M, N, K, act, _stream()), "tan_linear_bf16")
+    with _timed("linear", 2.0 * M * N * K):
+        check(lib().tan_linear_bf16(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+            _ptr(residual), residual.stride(0) if residual is not None else 0,
+            _ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+            _ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
+            M, N, K, act, _stream()), "tan_linear_bf16")
     _launches += 1
 
 
@@ -74,7 +107,8 @@ def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=Non
     a = LnArgs(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, d, _ptr(gamma), _ptr(beta), _ptr(add), add_rows,
                L_in, L_out, l_off, _ptr(out_f32), _ptr(out_bf16), l_split, strideA, strideB,
                _ptr(rawA), _ptr(rawB), _ptr(nrmA_bf16), _ptr(nrmB_bf16), _ptr(nrmA_f32), _ptr(nrmB_f32))
-    check(lib().tan_layernorm(C.byref(a), _stream()), "tan_layernorm")
+    with _timed("layernorm", float(rows) * d):
+        check(lib().tan_layernorm(C.byref(a), _stream()), "tan_layernorm")
     _launches += 1
 
 
@@ -82,9 +116,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kpm_u8: Optiona
               out: torch.Tensor, B: int, H: int, Lq: int, Lk: int) -> None:
     """tan_attention_bf16.  q/k/v/out are 2-D (possibly column-sliced) bf16 views [B*L, H*64]."""
     global _launches
-    check(lib().tan_attention_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
-                                   _ptr(kpm_u8), out.data_ptr(), out.stride(0), B, H, Lq, Lk, _stream()),
-          "tan_attention_bf16")
+    with _timed("attention", 4.0 * B * H * Lq * Lk * 64):
+        check(lib().tan_attention_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                       v.stride(0), _ptr(kpm_u8), out.data_ptr(), out.stride(0), B, H, Lq, Lk,
+                                       _stream()), "tan_attention_bf16")
     _launches += 1
 
 
@@ -99,10 +134,11 @@ def sim_workspace_bytes(g: SimGeom) -> int:
 def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride: int, g: SimGeom, start, end, col_valid, logits_out,
                 row_sums, col_sums, workspace) -> None:
     global _launches
-    check(lib().tan_sim_nce_fwd(vfeat.data_ptr(), tfeat.data_ptr(), tfeat_stage_stride, C.byref(g), start.data_ptr(),
-                                end.data_ptr(), col_valid.data_ptr(), _ptr(logits_out), row_sums.data_ptr(),
-                                col_sums.data_ptr(), workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-                                _stream()), "tan_sim_nce_fwd")
+    with _timed("sim_nce_fwd", 2.0 * g.B_loc * g.S * g.T * g.C * g.d):
+        check(lib().tan_sim_nce_fwd(vfeat.data_ptr(), tfeat.data_ptr(), tfeat_stage_stride, C.byref(g),
+                                    start.data_ptr(), end.data_ptr(), col_valid.data_ptr(), _ptr(logits_out),
+                                    row_sums.data_ptr(), col_sums.data_ptr(), workspace.data_ptr(),
+                                    workspace.numel() * workspace.element_size(), _stream()), "tan_sim_nce_fwd")
     _launches += 2
 
 
@@ -111,10 +147,11 @@ def nce_from_logits(logits, g: SimGeom, start, end, col_valid, row_sums, col_sum
     is_f32 = int(logits.dtype == torch.float32)
     if not is_f32 and logits.dtype != torch.bfloat16:
         raise _lib.TanError(f"nce_from_logits: logits must be fp32 or bf16, got {logits.dtype}")
-    check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), start.data_ptr(), end.data_ptr(),
-                                    col_valid.data_ptr(), row_sums.data_ptr(), col_sums.data_ptr(),
-                                    workspace.data_ptr(), workspace.numel() * workspace.element_size(), _stream()),
-          "tan_nce_from_logits")
+    with _timed("nce_from_logits", float(logits.numel()) * logits.element_size()):
+        check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), start.data_ptr(), end.data_ptr(),
+                                        col_valid.data_ptr(), row_sums.data_ptr(), col_sums.data_ptr(),
+                                        workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                                        _stream()), "tan_nce_from_logits")
     _launches += 2
 
 

@@ -1,0 +1,114 @@
+"""Step runner for the TAN hot path: one step = TemporalAligner.forward + get_loss (`--model init`)
+over one batch of clips.  Used by bench.py and the multi-GPU tests.
+
+  * `step_api(batch_host)`   the public API exactly as train/main.py:81-105 calls it, starting from
+                             HOST tensors / python lists: H2D copies, forward, get_loss, `.item()`.
+  * `step_resident()`        same kernels on inputs already resident in HBM, no host sync; with
+                             `use_graph=True` the whole step (about 100 kernel launches) is replayed
+                             from one CUDA graph, which removes the launch-bound gaps at small shapes.
+
+Multi-GPU (one process per GPU): each rank holds B_loc clips; the contrastive matrix spans the
+global batch (loss.py all-gathers text features / targets and all-reduces column sums).
+"""
+from __future__ import annotations
+
+import types
+from typing import Optional
+
+import torch
+
+from . import loss as loss_mod
+from . import ops, synth
+from .tan_model import TemporalAligner
+
+
+def default_loss_args():
+    return types.SimpleNamespace(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep",
+                                 loss_threshold=0.0, use_alignability_head=0, optim_policy="default")
+
+
+class TanStepRunner:
+    def __init__(self, num_encoder_layers=6, num_decoder_layers=6, B_loc=32, T=256, N=None, width=512,
+                 video_dim=1024, seed=888, device="cuda", rank=0, world_size=1, use_graph=True):
+        self.E, self.D, self.B, self.T = num_encoder_layers, num_decoder_layers, B_loc, T
+        self.N = N if N is not None else max(T // 8, 1)
+        self.width, self.video_dim = width, video_dim
+        self.device = torch.device(device)
+        self.rank, self.world = rank, world_size
+        self.shard = world_size > 1
+        self.use_graph = use_graph and world_size == 1
+        self.args = default_loss_args()
+        sd = synth.make_state_dict(self.E, self.D, width=width, d_in=video_dim, seed=seed, perturb=False)
+        self.model = TemporalAligner(self.E, self.D, random_pos_start=0, width=width, video_dim=video_dim)
+        self.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        self.model = self.model.to(self.device)
+        self.batch = synth.make_batch(B_loc, T, self.N, d_in=video_dim, seed=seed, tag=f"rank{rank}")
+        # pinned host copies (the e2e path starts here) and device-resident copies
+        self.h_video = torch.from_numpy(self.batch["video"]).pin_memory()
+        self.h_text = torch.from_numpy(self.batch["text"]).pin_memory()
+        self.h_vpm = torch.from_numpy(self.batch["video_padding_mask"]).pin_memory()
+        self.h_tpm = torch.from_numpy(self.batch["text_padding_mask"]).pin_memory()
+        self.d_video = self.h_video.to(self.device)
+        self.d_text = self.h_text.to(self.device)
+        self.d_vpm = self.h_vpm.to(self.device)
+        self.d_tpm = self.h_tpm.to(self.device)
+        self.input_data = {"start": self.batch["start"], "end": self.batch["end"], "text": self.batch["text_str"]}
+        self.nce = loss_mod.prepare_nce_inputs(self.batch["start"], self.batch["end"], self.d_tpm, T, self.N,
+                                               self.device, self.shard)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_video, self.h_text, self.h_vpm, self.h_tpm))
+        self.d2h_bytes = 4
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_loss = None
+        self.launches_per_step = None
+
+    # -- the public-API step, from host memory ------------------------------------------------------
+    def step_api(self) -> float:
+        dev = self.device
+        video = self.h_video.to(dev, non_blocking=True)
+        text = self.h_text.to(dev, non_blocking=True)
+        vpm = self.h_vpm.to(dev, non_blocking=True)
+        tpm = self.h_tpm.to(dev, non_blocking=True)
+        out = self.model(video, text, video_padding_mask=vpm, lang_padding_mask=tpm, text_timestamp=None,
+                         abs_text_pos=None)
+        ld = loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
+        return ld["loss"].item()                              # D2H read of the step's result
+
+    # -- device-resident step -----------------------------------------------------------------------
+    def _step_kernels(self) -> torch.Tensor:
+        out = self.model(self.d_video, self.d_text, video_padding_mask=self.d_vpm, lang_padding_mask=self.d_tpm)
+        l_dual = loss_mod.nce_loss_one_model(out["logits_dual"], self.nce, self.shard)
+        l_joint = loss_mod.nce_loss_one_model(out["logits_joint"], self.nce, self.shard)
+        return (l_dual + l_joint) / 2
+
+    def warmup(self, n=3):
+        for _ in range(n):
+            n0 = ops.launches()
+            loss = self._step_kernels()
+            self.launches_per_step = ops.launches() - n0
+        torch.cuda.synchronize()
+        if self.use_graph and self._graph is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_loss = self._step_kernels()
+            self._graph = g
+            g.replay()
+            torch.cuda.synchronize()
+        return float(loss)
+
+    def step_resident(self) -> torch.Tensor:
+        if self._graph is not None:
+            self._graph.replay()
+            return self._graph_loss
+        return self._step_kernels()
+
+    # -- work accounting -----------------------------------------------------------
+    def flops_per_clip(self, B_glob: Optional[int] = None) -> dict:
+        d, T, N, E, D = self.width, self.T, self.N, self.E, self.D
+        Bg = B_glob if B_glob is not None else self.B * self.world
+        f_layer = lambda L: 24 * L * d * d + 4 * L * L * d
+        pre = 2 * T * self.video_dim * d + 2 * N * 512 * d
+        enc = E * f_layer(T)
+        joint = D * f_layer(T + N)
+        sim = (E + D) * 2 * T * (Bg * N) * d
+        return {"pre": pre, "enc": enc, "joint": joint, "sim": sim, "total": pre + enc + joint + sim,
+                "gemm": pre + (E * T + D * (T + N)) * 24 * d * d}

@@ -1,0 +1,139 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: target/feature all-gather layout,
+global column indexing (b_off), additivity of the fixed-shift column sums across row shards, and the
+row (sum, count) reduction.  The per-rank exp-sums that the CUDA kernels would produce are computed
+here with the torch oracle formulas; everything else is the product's own code
+(loss.prepare_nce_inputs / gather_text_features / finish_loss)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import tan_oracle as O
+from temporalalignnet_b200 import synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _cpu_reduce(row_sums, col_sums, out4, do_rows=True, do_cols=True):
+    """torch restatement of tan_nce_reduce (checker for the CPU test)."""
+    R = row_sums.shape[1]
+    m = row_sums[1] > 0
+    out4[0] += (row_sums[0][m].log() - row_sums[1][m].log()).double().sum()
+    out4[1] += m.sum()
+    c = col_sums.reshape(2, -1)
+    m = c[1] > 0
+    out4[2] += (c[0][m].log() - c[1][m].log()).double().sum()
+    out4[3] += m.sum()
+
+
+def _exp_sums(vn, tn, nce, B_loc, S, T, N):
+    """What tan_sim_nce_fwd produces for local rows: vn [B_loc,S,T,d], tn [S,C,d] (global columns)."""
+    cos = torch.einsum("bstd,scd->bstc", vn, tn)
+    valid = nce.col_valid.bool()
+    e = torch.exp((cos - 1.0) / 0.07) * valid.float()
+    C = tn.shape[1]
+    tt = torch.arange(T).float()
+    pos_t = (nce.start[None] <= tt[:, None]) & (tt[:, None] < nce.end[None]) & valid[None]
+    own = (torch.arange(C) // N)[None] == (nce.b_off + torch.arange(B_loc))[:, None]
+    pe = e * (pos_t[None] & own[:, None, :])[:, None].float()
+    row = torch.stack((e.sum(-1).reshape(-1), pe.sum(-1).reshape(-1)))
+    col = torch.stack((e.sum(dim=(0, 2)), pe.sum(dim=(0, 2))))
+    return row.float(), col.float()
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from temporalalignnet_b200 import loss as L
+    torch.set_num_threads(2)
+    E = D = 2
+    Bg, T, N = 4, 16, 4
+    B_loc = Bg // world
+    sd = synth.make_state_dict(E, D, seed=5)
+    full = synth.make_batch(Bg, T, N, seed=5)
+    sl = slice(rank * B_loc, (rank + 1) * B_loc)
+    orc = O.TanOracle(sd, E, D)
+    video = torch.from_numpy(full["video"][sl])
+    text = torch.from_numpy(full["text"][sl])
+    vpm = torch.from_numpy(full["video_padding_mask"][sl])
+    tpm = torch.from_numpy(full["text_padding_mask"][sl])
+    # local features (each clip's encoders are independent of the other clips)
+    v = orc.get_visual_feature(video, vpm)
+    vn = v / v.norm(dim=-1, keepdim=True)
+    t = orc.get_textual_feature(text)
+    tn = (t / t.norm(dim=-1, keepdim=True)).reshape(B_loc * N, -1)
+    jv, jt = orc.get_joint_feature(video, vpm, t, tpm)
+    jvn = jv / jv.norm(dim=-1, keepdim=True)
+    jtn = (jt / jt.norm(dim=-1, keepdim=True)).permute(1, 0, 2, 3).reshape(D, B_loc * N, -1)
+    nce = L.prepare_nce_inputs(full["start"][sl], full["end"][sl], tpm, T, N, torch.device("cpu"), shard=True)
+    assert nce.b_off == rank * B_loc and nce.B_glob == Bg and nce.start.numel() == Bg * N
+    losses = []
+    for vfeat, tfeat, shared, S in ((vn, tn, True, E), (jvn, jtn, False, D)):
+        tg = L.gather_text_features(tfeat.contiguous(), shared, dist)
+        tg3 = tg[None].expand(S, -1, -1) if shared else tg
+        row, col = _exp_sums(vfeat, tg3, nce, B_loc, S, T, N)
+        losses.append(L.finish_loss(row, col.contiguous(), dist, reduce_fn=_cpu_reduce))
+    loss = float((losses[0] + losses[1]) / 2)
+    if rank == 0:
+        ref_out = orc.forward(torch.from_numpy(full["video"]), torch.from_numpy(full["text"]),
+                              full["video_padding_mask"], full["text_padding_mask"])
+        ref = float(O.get_loss_init(ref_out["logits_dual"], ref_out["logits_joint"], full["start"], full["end"],
+                                    full["text_padding_mask"])["loss"])
+        ret["loss"], ret["ref"] = loss, ref
+    gathered = [None] * world
+    dist.all_gather_object(gathered, loss)
+    if rank == 0:
+        ret["all"] = gathered
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_loss_equals_single_process_oracle():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert abs(ret["loss"] - ret["ref"]) < 1e-5 * abs(ret["ref"]), (ret["loss"], ret["ref"])
+    assert all(abs(x - ret["loss"]) < 1e-7 for x in ret["all"])      # every rank returns the global loss
+
+
+def test_prepare_nce_inputs_single_process_layout():
+    from temporalalignnet_b200 import loss as L
+    b = synth.make_batch(3, 20, 5, seed=2)
+    nce = L.prepare_nce_inputs(b["start"], b["end"], torch.from_numpy(b["text_padding_mask"]), 20, 5,
+                               torch.device("cpu"), shard=False)
+    mask, start, end = O.mask_from_time(b["start"], b["end"], 20, 5)
+    assert torch.equal(nce.start.view(3, 5), start) and torch.equal(nce.end.view(3, 5), end)
+    assert torch.equal(nce.col_valid.view(3, 5).bool(), ~torch.from_numpy(b["text_padding_mask"]))
+    m2, s2, e2 = L.get_mask_from_time(b["start"], b["end"], 20, 5, device="cpu")
+    assert torch.equal(m2[:, :mask.shape[1]], mask[:, :m2.shape[1]])
+
+
+def test_circulant_known_answer():
+    from temporalalignnet_b200.loss import circulant
+    assert circulant(torch.tensor([0, 1, 2]), dim=0).tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
+
+
+def test_state_dict_keys_match_reference_names():
+    from temporalalignnet_b200 import TemporalAligner, TwinTemporalAligner
+    m = TemporalAligner(2, 3, random_pos_start=0, use_alignability_head=1)
+    ref_keys = set(synth.make_state_dict(2, 3, use_alignability_head=True))
+    assert set(m.state_dict().keys()) == ref_keys
+    tw = TwinTemporalAligner(m=0.99, num_encoder_layers=1, num_decoder_layers=1)
+    assert all(k.startswith(("online.", "target.")) for k in tw.state_dict())
+    assert tw.target.random_pos_start == 0
+    p0 = [p.clone() for p in tw.target.parameters()]
+    for p in tw.online.parameters():
+        p.data.add_(1.0)
+    tw._momentum_update()
+    for a, b, o in zip(p0, tw.target.parameters(), tw.online.parameters()):
+        assert torch.allclose(b, a * 0.99 + o * 0.01, atol=1e-6)
