@@ -54,6 +54,12 @@ TAN_API const char* tan_last_error_string(void);
 /* TAN_OK if the current device is sm_100 (B200), TAN_ERR_ARCH otherwise, TAN_ERR_CUDA if no device. */
 TAN_API int tan_device_check(void);
 
+/* Development aid: point the GEMM kernels' per-CTA event trace at a device buffer of
+ * 64 * gridDim int64 slots (NULL disables it, the default).  Slot 0 = globaltimer at CTA start, slots 1-3
+ * = clock64 at start / after prologue / at exit, slots 4+6i.. = producer first/last issue, MMA first/last
+ * issue, epilogue start/end of the CTA's i-th tile. */
+TAN_API int tan_debug_set_trace(void* device_buffer);
+
 /* ---- dtype conversion ------------------------------------------------------------------------ */
 
 /* out[i] = bf16(in[i]), i < n.  Replaces the implicit fp32->half cast torch autocast inserts in
@@ -67,7 +73,7 @@ TAN_API int tan_cast_f32_to_bf16(const float* in, void* out, size_t n, void* str
  *   residual [M, N] fp32 (ldr) or NULL (may alias out_f32: each element is read before written),
  *   out_f32 [M, N] fp32 (ldo_f32) and/or out_bf16 [M, N] bf16 (ldo_bf16); at least one non-NULL.
  * tcgen05.mma (bf16 in, fp32 accumulate in TMEM), operands staged by TMA with 128-byte swizzle.
- * Requirements: K % 64 == 0, N % 32 == 0, lda/ldw % 8 == 0, 16-byte aligned bases.
+ * Requirements: K % 64 == 0, N % 128 == 0, lda/ldw % 8 == 0, 16-byte aligned bases, ld* % 4 == 0.
  * Replaces F.linear at: model/tan_model.py:155,:187,:233 (pre-projections), torch
  * nn/functional.py `_in_projection_packed` + out_proj reached from model/tfm_model.py:32 (QKV and
  * output projections, residual add of :36), model/tfm_model.py:23-27,:37 (c_fc + QuickGELU,

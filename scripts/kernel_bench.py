@@ -89,7 +89,29 @@ def bench_sim(B, S, T, N, d, Bglob, store):
     print(json.dumps(rec), flush=True)
 
 
+def sweep_linear():
+    M = 32 * 256
+    for (N, K, act, res, out) in ((1536, 512, 0, False, "bf16"), (512, 512, 0, True, "f32"),
+                                  (2048, 512, 1, False, "bf16"), (512, 2048, 0, True, "f32")):
+        for bn in (128, 256):
+            for cs in (1, 2, 4):
+                os.environ["TAN_GEMM_CS"], os.environ["TAN_GEMM_BN"] = str(cs), str(bn)
+                print(f"cs={cs} bn={bn} ", end="")
+                bench_linear(M, N, K, act=act, res=res, out=out)
+    os.environ.pop("TAN_GEMM_CS"); os.environ.pop("TAN_GEMM_BN")
+    for cs in (1, 2, 4):
+        os.environ["TAN_SIM_CS"] = str(cs)
+        print(f"cs={cs} ", end="")
+        bench_sim(32, 6, 256, 32, 512, 32, False)
+        print(f"cs={cs} ", end="")
+        bench_sim(32, 6, 256, 32, 512, 256, False)
+    os.environ.pop("TAN_SIM_CS")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        sweep_linear()
+        sys.exit(0)
     M = 32 * 256
     bench_linear(M, 512, 1024, out="f32")
     bench_linear(M, 1536, 512)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "tan_abi_version": (C.c_int, []),
     "tan_last_error_string": (C.c_char_p, []),
     "tan_device_check": (C.c_int, []),
+    "tan_debug_set_trace": (C.c_int, [C.c_void_p]),
     "tan_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tan_linear_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,

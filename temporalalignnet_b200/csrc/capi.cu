@@ -7,6 +7,8 @@
 
 namespace tanb {
 
+__device__ long long* g_gemm_trace = nullptr;
+
 static thread_local char g_err[512] = "";
 
 int set_error(int code, const char* fmt, ...) {
@@ -117,6 +119,13 @@ extern "C" int tan_device_check(void) {
   if (d->checked != 1)
     return set_error(TAN_ERR_ARCH, "device is sm_%d%d; this library only contains sm_100a (B200) code", d->major,
                      d->minor);
+  return TAN_OK;
+}
+
+extern "C" int tan_debug_set_trace(void* device_buffer) {
+  TAN_CHECK(tan_device_check());
+  long long* p = static_cast<long long*>(device_buffer);
+  TAN_CUDA(cudaMemcpyToSymbol(g_gemm_trace, &p, sizeof(p)));
   return TAN_OK;
 }
 

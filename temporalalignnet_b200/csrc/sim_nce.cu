@@ -11,6 +11,8 @@
 //
 // All sums use the fixed shift 1/0.07 (cosines are bounded by 1), so no running max is needed and
 // partial sums from different tiles / ranks add directly:  e = exp((cos - 1)/0.07) in (0, 1].
+#include <cstdlib>
+
 #include "umma_gemm.cuh"
 
 namespace tanb {
@@ -49,13 +51,26 @@ template <int BN>
 struct SimEpi {
   // per-quarter column partials: [4 quarters][2 (all,pos)][BN]
   static constexpr int kExtraSmem = 4 * 2 * BN * 4;
+  struct State {};
   SimCommon c;
+  int cs;                  // cluster size; (B_loc * seg_tiles) % cs == 0 so a cluster never straddles a stage
   int64_t b_stage_rows;    // rows of B per stage in the B tensor map (0 for the dual encoder)
   bf16* logits;            // optional [R, C]
   float* row_part;         // [2][n_tiles][R]
   float* col_part;         // [2][m_tiles][C]
 
-  __device__ __forceinline__ int num_tiles() const { return c.m_tiles * c.n_tiles; }
+  __device__ __forceinline__ int num_ctiles() const { return (c.m_tiles / cs) * c.n_tiles; }
+  // Cluster tiles walk the row tiles STAGE-major (s, b, i) so that the cs row tiles of a cluster share
+  // the stage (= the same B tile); the returned tile id is in the natural (b, s, i) numbering.
+  __device__ __forceinline__ int tile_id(int ct, int rank) const {
+    const int tn = ct % c.n_tiles;
+    const int q = (ct / c.n_tiles) * cs + rank;                 // index in (s, b, i) order
+    const int per_stage = c.g.B_loc * c.seg_tiles;
+    const int s = q / per_stage, rem = q % per_stage;
+    const int b = rem / c.seg_tiles, i = rem % c.seg_tiles;
+    const int tm = (b * c.g.S + s) * c.seg_tiles + i;
+    return tm * c.n_tiles + tn;
+  }
   __device__ __forceinline__ TileCoord coord(int tile) const {
     const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
     const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
@@ -65,7 +80,11 @@ struct SimEpi {
     return tc;
   }
 
-  __device__ __forceinline__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch) const {
+  __device__ __forceinline__ void init(uint8_t*) const {}
+  __device__ __forceinline__ void pre(int, int, int, uint8_t*, State&) const {}
+
+  __device__ __forceinline__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch,
+                                      State&) const {
     const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
     const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
     const int t = i * kGemmBM + quarter * 32 + lane;          // frame index of this thread's row
@@ -191,17 +210,38 @@ __global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Statistics from materialised logits.
-// CTA = 8 warps; a CTA owns a (segment, 256-column slab) and walks the segment's T rows, warp w
-// taking rows w, w+8, ...  Each lane owns 8 consecutive columns (one 16-byte load of bf16, two of
-// fp32), so a warp reads 512 contiguous bytes per row; column sums live in registers for the whole
-// walk; row sums need one shuffle reduction per row.
+// Statistics from materialised logits (HBM-bound).
+// CTA = 8 warps; a CTA owns a (segment, 256-column slab) and walks the segment's T rows.  Each lane owns
+// 8 consecutive columns (one 16-byte load of bf16, two of fp32), so a warp reads 512 contiguous bytes
+// per row.  A warp takes kNceRows rows per iteration and issues all their loads before touching any of
+// them (memory-level parallelism: 8 x 512 B in flight per warp); column sums live in registers for the
+// whole walk; the kNceRows row sums are reduced together by one transposing butterfly (9 shuffles for 8
+// values instead of 5 per value).
 // ---------------------------------------------------------------------------------------------
 constexpr int kNceCols = 256;
 constexpr int kNceWarps = 8;
+constexpr int kNceRows = 8;
+
+// v[i] (i < 8) per lane -> lane l returns sum over the warp of v[l & 7] (valid in every lane).
+__device__ __forceinline__ float warp_sum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float keep = upper ? v[j + half] : v[j];
+      const float send = upper ? v[j] : v[j + half];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  float r = v[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
 
 template <bool F32>
-__global__ void __launch_bounds__(kNceWarps * 32)
+__global__ void __launch_bounds__(kNceWarps * 32, 2)
 nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, float* __restrict__ row_part,
                        float* __restrict__ col_sums_part) {
   __shared__ float scol[kNceWarps][2][kNceCols];
@@ -211,65 +251,96 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, float* __re
   const int col0 = slab * kNceCols + lane * 8;
   const int bg = c.g.b_off + seg / c.g.S;
   const int pos_c0 = bg * c.g.N, pos_c1 = pos_c0 + c.g.N;
-  const bool aligned = (c.g.C % 8) == 0;
+  const bool aligned = (c.g.C % 8) == 0 && col0 + 8 <= c.g.C;
+  const bool slab_has_pos = slab * kNceCols < pos_c1 && (slab + 1) * kNceCols > pos_c0;   // CTA-uniform
 
-  bool ok[8];
+  uint32_t okbits = 0;
   float st[8], en[8];
-  bool any_pos_col = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int col = col0 + j;
-    ok[j] = col < c.g.C && c.col_valid[col] != 0;
-    const bool pc = ok[j] && col >= pos_c0 && col < pos_c1;
+    const bool ok = col < c.g.C && c.col_valid[col] != 0;
+    okbits |= ok ? (1u << j) : 0u;
+    const bool pc = ok && col >= pos_c0 && col < pos_c1;
     st[j] = pc ? c.start[col] : 1.f;
-    en[j] = pc ? c.end[col] : 0.f;
-    any_pos_col |= pc;
+    en[j] = pc ? c.end[col] : 0.f;             // start >= end: never positive
   }
   float call[8], cpos[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { call[j] = 0.f; cpos[j] = 0.f; }
 
-  for (int t = warp; t < c.g.T; t += kNceWarps) {
-    const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
-    float x[8];
-    if (aligned && col0 + 8 <= c.g.C) {
-      if (F32) {
-        const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(logits) + r * c.g.C + col0);
-        const float4 a = p[0], b = p[1];
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  for (int t0 = warp * kNceRows; t0 < c.g.T; t0 += kNceWarps * kNceRows) {
+    // ---- issue every load of this row group first (raw 16-byte words: 4 (bf16) / 8 (fp32) registers per row)
+    uint4 raw[kNceRows][F32 ? 2 : 1];
+#pragma unroll
+    for (int i = 0; i < kNceRows; ++i) {
+      const int t = t0 + i;
+      const int64_t r = static_cast<int64_t>(seg) * c.g.T + (t < c.g.T ? t : c.g.T - 1);
+      if (aligned) {
+        if (F32) {
+          const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(logits) + r * c.g.C + col0);
+          raw[i][0] = __ldcs(p);
+          raw[i][F32 ? 1 : 0] = __ldcs(p + 1);
+        } else {
+          raw[i][0] = __ldcs(reinterpret_cast<const uint4*>(static_cast<const bf16*>(logits) + r * c.g.C + col0));
+        }
       } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const bf16*>(logits) + r * c.g.C + col0);
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        float xs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int col = col0 + j;
+          xs[j] = 0.f;
+          if (col < c.g.C)
+            xs[j] = F32 ? static_cast<const float*>(logits)[r * c.g.C + col]
+                        : __bfloat162float(static_cast<const bf16*>(logits)[r * c.g.C + col]);
+        }
+        if (F32) {
+          raw[i][0] = make_uint4(__float_as_uint(xs[0]), __float_as_uint(xs[1]), __float_as_uint(xs[2]), __float_as_uint(xs[3]));
+          raw[i][F32 ? 1 : 0] = make_uint4(__float_as_uint(xs[4]), __float_as_uint(xs[5]), __float_as_uint(xs[6]), __float_as_uint(xs[7]));
+        } else {
+          raw[i][0] = make_uint4(pack_bf16x2(xs[0], xs[1]), pack_bf16x2(xs[2], xs[3]), pack_bf16x2(xs[4], xs[5]),
+                                 pack_bf16x2(xs[6], xs[7]));
+        }
+      }
+    }
+    // ---- consume
+    float ra[kNceRows], rp[kNceRows];
+#pragma unroll
+    for (int i = 0; i < kNceRows; ++i) {
+      float x[8];
+      if (F32) {
+        x[0] = __uint_as_float(raw[i][0].x); x[1] = __uint_as_float(raw[i][0].y);
+        x[2] = __uint_as_float(raw[i][0].z); x[3] = __uint_as_float(raw[i][0].w);
+        x[4] = __uint_as_float(raw[i][F32 ? 1 : 0].x); x[5] = __uint_as_float(raw[i][F32 ? 1 : 0].y);
+        x[6] = __uint_as_float(raw[i][F32 ? 1 : 0].z); x[7] = __uint_as_float(raw[i][F32 ? 1 : 0].w);
+      } else {
+        const float2 a = unpack_bf16x2(raw[i][0].x), b = unpack_bf16x2(raw[i][0].y);
+        const float2 cc = unpack_bf16x2(raw[i][0].z), d = unpack_bf16x2(raw[i][0].w);
         x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = cc.x; x[5] = cc.y; x[6] = d.x; x[7] = d.y;
       }
-    } else {
+      const bool row_ok = t0 + i < c.g.T;
+      const float tf = static_cast<float>(t0 + i);
+      ra[i] = 0.f;
+      rp[i] = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int col = col0 + j;
-        x[j] = 0.f;
-        if (col < c.g.C)
-          x[j] = F32 ? static_cast<const float*>(logits)[r * c.g.C + col]
-                     : __bfloat162float(static_cast<const bf16*>(logits)[r * c.g.C + col]);
+        const float e = (((okbits >> j) & 1u) && row_ok) ? fast_exp2(fmaf(x[j], kExpScale, -kExpScale)) : 0.f;
+        call[j] += e;
+        ra[i] += e;
+        if (slab_has_pos) {
+          const float pe = (st[j] <= tf && tf < en[j]) ? e : 0.f;
+          cpos[j] += pe;
+          rp[i] += pe;
+        }
       }
     }
-    const float tf = static_cast<float>(t);
-    float ra = 0.f, rp = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float e = ok[j] ? fast_exp2(fmaf(x[j], kExpScale, -kExpScale)) : 0.f;
-      call[j] += e;
-      ra += e;
-      if (any_pos_col) {
-        const float pe = (st[j] <= tf && tf < en[j]) ? e : 0.f;
-        cpos[j] += pe;
-        rp += pe;
-      }
-    }
-    ra = warp_sum(ra);
-    rp = warp_sum(rp);
-    if (lane == 0) {
-      row_part[(static_cast<int64_t>(0) * gridDim.x + slab) * c.R + r] = ra;
-      row_part[(static_cast<int64_t>(1) * gridDim.x + slab) * c.R + r] = rp;
+    const float ra_sum = warp_sum8(ra, lane);
+    float rp_sum = 0.f;
+    if (slab_has_pos) rp_sum = warp_sum8(rp, lane);
+    if (lane < kNceRows && t0 + lane < c.g.T) {
+      const int64_t r = static_cast<int64_t>(seg) * c.g.T + t0 + lane;
+      row_part[(static_cast<int64_t>(0) * gridDim.x + slab) * c.R + r] = ra_sum;
+      row_part[(static_cast<int64_t>(1) * gridDim.x + slab) * c.R + r] = rp_sum;
     }
   }
 #pragma unroll
@@ -357,23 +428,6 @@ static int pick_bn(const tan_sim_geom* g) {
 
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-template <int BN>
-static int launch_sim(const CUtensorMap& tmA, const CUtensorMap& tmB, SimEpi<BN> epi, int d, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = umma_gemm_kernel<BN, SimEpi<BN>>;
-  constexpr int smem = Cfg::kSmemBytes + SimEpi<BN>::kExtraSmem;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  const int tiles = epi.c.m_tiles * epi.c.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, smem, st>>>(tmA, tmB, epi, d / kGemmBK);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
-}
-
 }  // namespace tanb
 
 using namespace tanb;
@@ -410,23 +464,39 @@ extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfe
   float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
                                              align256(2 * static_cast<size_t>(c.n_tiles) * c.R * 4));
   const int64_t b_rows = tfeat_stage_stride == 0 ? g->C : static_cast<int64_t>(g->S) * g->C;
+  // cluster size along M (B-tile multicast): the row tiles of one stage must split evenly
+  int cs = 2;
+  if (const char* e = getenv("TAN_SIM_CS")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) cs = v;
+  }
+  while (cs > 1 && (g->B_loc * c.seg_tiles) % cs != 0) cs >>= 1;
   CUtensorMap tmA, tmB;
   TAN_CHECK(make_tmap_2d_bf16(&tmA, vfeat, c.R, g->d, g->d, kGemmBM, kGemmBK));
-  TAN_CHECK(make_tmap_2d_bf16(&tmB, tfeat, b_rows, g->d, g->d, bn, kGemmBK));
+  TAN_CHECK(make_tmap_2d_bf16(&tmB, tfeat, b_rows, g->d, g->d, bn / cs, kGemmBK));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TAN_LAUNCH_SIM(BN_)                                                          \
-  {                                                                                  \
-    SimEpi<BN_> e;                                                                   \
-    e.c = c;                                                                         \
-    e.b_stage_rows = tfeat_stage_stride == 0 ? 0 : g->C;                             \
-    e.logits = static_cast<bf16*>(logits_out);                                       \
-    e.row_part = row_part;                                                           \
-    e.col_part = col_part;                                                           \
-    TAN_CHECK(launch_sim<BN_>(tmA, tmB, e, g->d, st));                               \
+#define TAN_LAUNCH_SIM(BN_, CS_)                                                                      \
+  {                                                                                                   \
+    SimEpi<BN_> e;                                                                                    \
+    e.c = c;                                                                                          \
+    e.cs = CS_;                                                                                       \
+    e.b_stage_rows = tfeat_stage_stride == 0 ? 0 : g->C;                                              \
+    e.logits = static_cast<bf16*>(logits_out);                                                        \
+    e.row_part = row_part;                                                                            \
+    e.col_part = col_part;                                                                            \
+    TAN_CHECK((launch_umma_gemm<BN_, CS_, SimEpi<BN_>>(tmA, tmB, e, (c.m_tiles / CS_) * c.n_tiles,    \
+                                                        g->d / kGemmBK, st)));                        \
   }
-  if (bn == 256) TAN_LAUNCH_SIM(256)
-  else if (bn == 128) TAN_LAUNCH_SIM(128)
-  else TAN_LAUNCH_SIM(64)
+#define TAN_LAUNCH_SIM_CS(BN_)                  \
+  {                                             \
+    if (cs == 4) TAN_LAUNCH_SIM(BN_, 4)         \
+    else if (cs == 2) TAN_LAUNCH_SIM(BN_, 2)    \
+    else TAN_LAUNCH_SIM(BN_, 1)                 \
+  }
+  if (bn == 256) TAN_LAUNCH_SIM_CS(256)
+  else if (bn == 128) TAN_LAUNCH_SIM_CS(128)
+  else TAN_LAUNCH_SIM_CS(64)
+#undef TAN_LAUNCH_SIM_CS
 #undef TAN_LAUNCH_SIM
   const int64_t total = 2 * c.R + 2ll * g->S * g->C;
   int blocks = static_cast<int>((total + 255) / 256);

@@ -3,14 +3,22 @@
 //
 //   D[128 x BN] (fp32, TMEM) = A[128 x K] (bf16, K-major) * B[BN x K]^T (bf16, K-major)
 //
-// Roles (256 threads, one CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [128 x 64] (A) and [BN x 64] (B),
+// Roles (256 threads, one CTA per SM, static round-robin tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [128 x 64] (A) and [BN/CS x 64] (B),
 //               128-byte swizzle, STAGES-deep ring guarded by full/empty mbarriers
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
 //               4 per 64-wide K block; tcgen05.commit releases the smem slot / publishes the tile
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns) and deallocator
 //   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> Epi functor; the next
 //               tile's MMAs run meanwhile on the other accumulator stage
+//
+// Thread-block clusters (CS = 1, 2 or 4 CTAs along M).  The CS CTAs of a cluster work on CS different
+// 128-row blocks that share the same B tile.  Each CTA fetches only BN/CS rows of B and TMA-multicasts
+// them into the same smem slot of every CTA in the cluster, so the B operand crosses the L2->SM fabric
+// once per cluster instead of once per CTA (measured: these GEMMs are bound by L2->SM bytes, ~6-7 TB/s
+// chip-wide, not by the tensor pipe; bytes per CTA per K block drop from 16+32 KB to 16+32/CS KB).
+// A slot may be overwritten only when every CTA of the cluster has consumed it: tcgen05.commit
+// multicasts its arrival to the empty barrier of all CS CTAs (count CS).
 //
 // HBM/L2 layout: A rows and B rows are both K-contiguous (nn.Linear weight layout needs no
 // transpose).  K % 64 == 0.  M/N tails are zero-filled by TMA on load and masked by the Epi.
@@ -38,26 +46,65 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
 };
 
+// Optional per-CTA event trace (development aid): tan_debug_set_trace() points this at a device buffer of
+// 64 int64 slots per CTA; slot 0 = globaltimer at start, others = clock64 stamps (see TRACE() sites).
+extern __device__ long long* g_gemm_trace;
+__device__ __forceinline__ void trace_evt(long long* tr, int slot) {
+  if (tr != nullptr && slot < 64) tr[blockIdx.x * 64 + slot] = clock64();
+}
+
 struct TileCoord {
   int a_row;   // TMA row coordinate of the A box
-  int b_row;   // TMA row coordinate of the B box
+  int b_row;   // TMA row coordinate of the (full, BN-row) B tile; identical for all CTAs of a cluster
 };
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0,
+                                                  int crd1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 
 // Epi concept:
 //   static constexpr int kExtraSmem;                         bytes of epilogue scratch
-//   __device__ int  num_tiles() const;
+//   struct State;                                            per-thread registers carried from pre() to run()
+//   __device__ int  num_ctiles() const;                      number of cluster tiles (CS row blocks x one B tile)
+//   __device__ int  tile_id(int ctile, int cta_rank) const;  this CTA's tile inside cluster tile `ctile`
 //   __device__ TileCoord coord(int tile) const;
-//   __device__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch);
+//   __device__ void init(uint8_t* scratch) const;            all 256 threads, before the role split
+//   __device__ void pre(int tile, int quarter, int lane, uint8_t* scratch, State&) const;
+//        epilogue threads, BEFORE waiting for the accumulator: issue loads that do not depend on it
+//   __device__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch, State&) const;
 //        called by all 128 epilogue threads; must read its accumulator via tmem_ld_32x32 at
 //        tmem_acc + (quarter*32 << 16) + column and finish with tmem_ld_wait() before returning.
-template <int BN, class Epi>
+template <int BN, int CS, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const Epi epi, const int num_kb) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1);
+  constexpr int kBSliceRows = BN / CS;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B atoms
+  // 1024-byte alignment for SWIZZLE_128B atoms (identical offset in every CTA of the cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
@@ -71,7 +118,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = epi.num_tiles();
+  const int cta_rank = (CS > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CS;
+  const int num_clusters = gridDim.x / CS;
+  const int num_ctiles = epi.num_ctiles();
+  long long* const tr = g_gemm_trace;
+  if (tr != nullptr && threadIdx.x == 0) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tr[blockIdx.x * 64 + 0] = gt;
+    trace_evt(tr, 1);
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -80,7 +137,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CS);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -92,23 +149,34 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  epi.init(epi_scratch);
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();                 // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) trace_evt(tr, 2);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc = epi.coord(tile);
+      int it = 0;
+      for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
+        const TileCoord tc = epi.coord(epi.tile_id(ct, cta_rank));
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);           // every CTA of the cluster has consumed this slot
+          if (kb == 0) trace_evt(tr, 4 + it * 6 + 0);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kGemmBK, tc.a_row);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kGemmBK, tc.b_row);
+          if (CS == 1) {
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kGemmBK, tc.b_row);
+          } else {
+            tma_load_2d_mcast(smem_b + stage * Cfg::kBBytes + cta_rank * (kBSliceRows * 128), &tmB, &full_bar[stage],
+                              kb * kGemmBK, tc.b_row + cta_rank * kBSliceRows, kMask);
+          }
+          if (kb == num_kb - 1) trace_evt(tr, 4 + it * 6 + 1);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -121,14 +189,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);            // TMA bytes have landed
+        mbar_wait(&full_bar[stage], phase);            // own A + all CS slices of B have landed
         tc_fence_after();
         if (lane == 0) {
+          if (kb == 0) trace_evt(tr, 4 + it * 6 + 2);
           const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
@@ -136,8 +206,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the >>4 address field
             umma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);                // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) tc_commit(&tmem_full[acc]);
+          // slot reusable once these MMAs retire -- tell every CTA of the cluster
+          if (CS == 1) tc_commit(&empty_bar[stage]);
+          else tc_commit_mcast(&empty_bar[stage], kMask);
+          if (kb == num_kb - 1) {
+            tc_commit(&tmem_full[acc]);
+            trace_evt(tr, 4 + it * 6 + 3);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -149,12 +224,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may address
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int ct = cluster_id; ct < num_ctiles; ct += num_clusters, ++it) {
+      const int tile = epi.tile_id(ct, cta_rank);
+      typename Epi::State st;
+      epi.pre(tile, quarter, lane, epi_scratch, st);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epi.run(tile, tmem_base + acc * BN, quarter, lane, epi_scratch);
+      if (threadIdx.x == kEpiWarp0 * 32) trace_evt(tr, 4 + it * 6 + 4);
+      epi.run(tile, tmem_base + acc * BN, quarter, lane, epi_scratch, st);
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == kEpiWarp0 * 32) trace_evt(tr, 4 + it * 6 + 5);
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -162,10 +243,50 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();                 // no CTA exits while peers may still signal its barriers
+  if (threadIdx.x == 0) trace_evt(tr, 3);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+// Launch helper: cluster dimension CS along x; grid = clusters * CS.
+template <int BN, int CS, class Epi>
+int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi& epi, int num_ctiles, int num_kb,
+                     cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = umma_gemm_kernel<BN, CS, Epi>;
+  constexpr int smem = Cfg::kSmemBytes + Epi::kExtraSmem;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    TAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CS;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  // persistent grid = the number of clusters that can be co-resident (GPC sizes may strand a few SMs)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(num_sms() / CS * CS, 1, 1);
+    if (CS == 1 || cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) n = num_sms() / CS;
+    (void)cudaGetLastError();
+    max_clusters = n < num_sms() / CS ? n : num_sms() / CS;
+  }
+  const int clusters = num_ctiles < max_clusters ? num_ctiles : max_clusters;
+  cfg.gridDim = dim3(clusters * CS, 1, 1);
+  TAN_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, epi, num_kb));
+  return TAN_OK;
 }
 
 }  // namespace tanb

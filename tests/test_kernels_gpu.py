@@ -34,7 +34,7 @@ def test_cast():
 
 @pytest.mark.parametrize("M,N,K", [
     (128, 256, 64), (128, 128, 512), (256, 512, 512), (8192, 512, 512), (1000, 1536, 512),
-    (77, 2048, 512), (4608, 512, 2048), (300, 768, 3072), (128, 32, 64), (9216, 1536, 512),
+    (77, 2048, 512), (4608, 512, 2048), (300, 768, 3072), (128, 128, 64), (9216, 1536, 512), (33, 384, 128),
 ])
 def test_linear_plain(M, N, K):
     ops = _ops()
@@ -94,7 +94,11 @@ def test_linear_rejects_bad_shapes():
     from temporalalignnet_b200 import TanError
     ops = _ops()
     a = torch.zeros(128, 100, dtype=torch.bfloat16, device=DEV)      # K % 64 != 0
-    w = torch.zeros(64, 100, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(128, 100, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(TanError, match="TAN_ERR_SHAPE"):
+        ops.linear(a, w, out_f32=torch.empty(128, 128, device=DEV))
+    a = torch.zeros(128, 128, dtype=torch.bfloat16, device=DEV)      # N % 128 != 0
+    w = torch.zeros(64, 128, dtype=torch.bfloat16, device=DEV)
     with pytest.raises(TanError, match="TAN_ERR_SHAPE"):
         ops.linear(a, w, out_f32=torch.empty(128, 64, device=DEV))
 
