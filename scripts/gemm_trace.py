@@ -34,11 +34,14 @@ def us(c): return c / 1e3 / clk
 rel = lambda col: us(t[:, col] - t[:, 1])
 print(f"prologue done: median {np.median(rel(2)):.2f} us  max {rel(2).max():.2f}")
 print(f"kernel exit:   median {np.median(rel(3)):.2f} us  max {rel(3).max():.2f}")
-names = ["prod_first", "prod_last", "mma_first", "mma_last", "epi_start", "epi_end"]
-for it in range(6):
-    cols = [4 + it * 6 + j for j in range(6)]
+names = ["prod_first", "prod_last", "mma_first", "mma_last", "epi_pre", "epi_bufs_free", "epi_acc_ready", "epi_end"]
+for it in range(3):
+    cols = [4 + it * 8 + j for j in range(8)]
     have = t[:, cols[0]] != 0
     if not have.any():
         break
-    s = " ".join(f"{n}={np.median(us(t[have][:, c] - t[have][:, 1])):6.2f}" for n, c in zip(names, cols))
+    def med(c):
+        ok = have & (t[:, c] != 0)
+        return np.median(us(t[ok][:, c] - t[ok][:, 1])) if ok.any() else float("nan")
+    s = " ".join(f"{n}={med(c):6.2f}" for n, c in zip(names, cols))
     print(f"tile {it} ({have.sum():3d} CTAs): {s}")

@@ -30,6 +30,28 @@ def timeit(fn, iters=10, warm=3):
     return ts[len(ts) // 2]
 
 
+def timeit_chain(fn, n=20, iters=5):
+    """Steady-state per-launch time: a CUDA graph of n back-to-back launches (warm L2, PDL overlap)."""
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / n)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def bench_linear(M, N, K, act=0, res=False, out="bf16"):
     a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
     w = (torch.randn(N, K, device=DEV) * K ** -0.5).to(torch.bfloat16)
@@ -39,9 +61,15 @@ def bench_linear(M, N, K, act=0, res=False, out="bf16"):
     ob = torch.empty(M, N, dtype=torch.bfloat16, device=DEV) if out == "bf16" else None
     ms = timeit(lambda: ops.linear(a, w, bias=bias, residual=r, out_f32=of if not res else r, out_bf16=ob, act=act))
     ms_t = timeit(lambda: torch.matmul(a, w.t()))
+    ms_c = timeit_chain(lambda: ops.linear(a, w, bias=bias, residual=r, out_f32=of if not res else r, out_bf16=ob, act=act))
+    oc = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ms_tc = timeit_chain(lambda: torch.matmul(a, w.t(), out=oc))
     print(json.dumps({"kernel": "linear", "M": M, "N": N, "K": K, "act": act, "res": res, "ms": round(ms, 4),
                       "tflops": round(2 * M * N * K / ms / 1e9, 1), "cublas_ms": round(ms_t, 4),
-                      "cublas_tflops": round(2 * M * N * K / ms_t / 1e9, 1)}), flush=True)
+                      "cublas_tflops": round(2 * M * N * K / ms_t / 1e9, 1),
+                      "chain_ms": round(ms_c, 4), "chain_tflops": round(2 * M * N * K / ms_c / 1e9, 1),
+                      "cublas_chain_ms": round(ms_tc, 4), "cublas_chain_tflops": round(2 * M * N * K / ms_tc / 1e9, 1)}),
+          flush=True)
 
 
 def bench_attn(B, H, L):
@@ -50,8 +78,10 @@ def bench_attn(B, H, L):
     out = torch.empty(B * L, d, dtype=torch.bfloat16, device=DEV)
     ms = timeit(lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, out, B, H, L, L))
     fl = 4 * B * H * L * L * 64
+    ms_c = timeit_chain(lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, out, B, H, L, L))
     print(json.dumps({"kernel": "attention", "B": B, "H": H, "L": L, "ms": round(ms, 4),
-                      "tflops": round(fl / ms / 1e9, 1)}), flush=True)
+                      "tflops": round(fl / ms / 1e9, 1), "chain_ms": round(ms_c, 4),
+                      "chain_tflops": round(fl / ms_c / 1e9, 1)}), flush=True)
 
 
 def bench_ln(rows, d):
@@ -59,8 +89,10 @@ def bench_ln(rows, d):
     g, b = torch.ones(d, device=DEV), torch.zeros(d, device=DEV)
     ob = torch.empty(rows, d, dtype=torch.bfloat16, device=DEV)
     ms = timeit(lambda: ops.layernorm(x, rows, d, gamma=g, beta=b, out_bf16=ob))
+    ms_c = timeit_chain(lambda: ops.layernorm(x, rows, d, gamma=g, beta=b, out_bf16=ob))
     print(json.dumps({"kernel": "layernorm", "rows": rows, "d": d, "ms": round(ms, 4),
-                      "GBps": round(rows * d * 6 / ms / 1e6, 1)}), flush=True)
+                      "GBps": round(rows * d * 6 / ms / 1e6, 1), "chain_ms": round(ms_c, 4),
+                      "chain_GBps": round(rows * d * 6 / ms_c / 1e6, 1)}), flush=True)
 
 
 def bench_sim(B, S, T, N, d, Bglob, store):
@@ -113,6 +145,13 @@ if __name__ == "__main__":
         sweep_linear()
         sys.exit(0)
     M = 32 * 256
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "attn":
+        bench_attn(32, 8, 256)
+        bench_attn(32, 8, 288)
+        bench_attn(4, 12, 1152)
+        bench_ln(M, 512)
+        sys.exit(0)
     bench_linear(M, 512, 1024, out="f32")
     bench_linear(M, 1536, 512)
     bench_linear(M, 512, 512, res=True, out="f32")
@@ -120,6 +159,8 @@ if __name__ == "__main__":
     bench_linear(M, 512, 2048, res=True, out="f32")
     bench_linear(32 * 288, 1536, 512)
     bench_linear(32 * 288, 2048, 512, act=1)
+    if only == "linear":
+        sys.exit(0)
     bench_attn(32, 8, 256)
     bench_attn(32, 8, 288)
     bench_attn(4, 12, 1152)

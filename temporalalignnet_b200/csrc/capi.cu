@@ -2,6 +2,7 @@
 // encoding, dtype cast.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -71,28 +72,46 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_rows, uint32_t box_cols) {
+// elem_bytes: 2 (bf16) or 4 (fp32); the box is always 128 bytes wide (the 128-byte swizzle span).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return set_error(TAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+  if (elem_bytes != 2 && elem_bytes != 4) return set_error(TAN_ERR_ARG, "make_tmap_2d: element size must be 2 or 4");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elem_bytes) % 16 != 0)
     return set_error(TAN_ERR_SHAPE, "TMA operand needs a 16-byte aligned base and row pitch");
-  if (box_cols * 2 != 128 || box_rows > 256)
-    return set_error(TAN_ERR_SHAPE, "TMA box must be 64 bf16 wide and at most 256 rows");
+  if (box_rows == 0 || box_rows > 256) return set_error(TAN_ERR_SHAPE, "TMA box must have 1..256 rows");
   const cuuint64_t gdim[2] = {cols, rows};
-  const cuuint64_t gstride[1] = {ld * 2};
-  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint64_t gstride[1] = {ld * elem_bytes};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
   const cuuint32_t estride[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(TAN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return TAN_OK;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  if (box_cols * 2 != 128) return set_error(TAN_ERR_SHAPE, "TMA box must be 64 bf16 wide");
+  return make_tmap_2d(out, base, 2, rows, cols, ld, box_rows);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TAN_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 __global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint4* __restrict__ out, size_t n8) {
   size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  pdl_launch_dependents();
+  pdl_wait();
   for (; i < n8; i += stride) {
     const float4 a = __ldg(in + 2 * i);
     const float4 b = __ldg(in + 2 * i + 1);
@@ -139,8 +158,7 @@ extern "C" int tan_cast_f32_to_bf16(const float* in, void* out, size_t n, void* 
   size_t blocks = (n8 + 255) / 256;
   const size_t cap = static_cast<size_t>(num_sms()) * 8;
   if (blocks > cap) blocks = cap;
-  cast_f32_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(in), reinterpret_cast<uint4*>(out), n8);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
+  return launch_pdl(cast_f32_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                    static_cast<cudaStream_t>(stream), 1, reinterpret_cast<const float4*>(in),
+                    reinterpret_cast<uint4*>(out), n8);
 }

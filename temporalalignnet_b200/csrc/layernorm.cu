@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const tan_ln_args a) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int d = a.d;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < a.rows; r += gridDim.x * warps_per_block) {
     float x[V * 4];
     if (a.in_is_bf16) {
@@ -128,14 +130,14 @@ extern "C" int tan_layernorm(const tan_ln_args* args, void* stream) {
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (a.d / 128) {
-    case 1: layernorm_kernel<1><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 2: layernorm_kernel<2><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 3: layernorm_kernel<3><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 4: layernorm_kernel<4><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 5: layernorm_kernel<5><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 6: layernorm_kernel<6><<<blocks, warps * 32, 0, st>>>(a); break;
-    case 7: layernorm_kernel<7><<<blocks, warps * 32, 0, st>>>(a); break;
-    default: layernorm_kernel<8><<<blocks, warps * 32, 0, st>>>(a); break;
+    case 1: TAN_CHECK(launch_pdl(layernorm_kernel<1>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 2: TAN_CHECK(launch_pdl(layernorm_kernel<2>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 3: TAN_CHECK(launch_pdl(layernorm_kernel<3>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 4: TAN_CHECK(launch_pdl(layernorm_kernel<4>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 5: TAN_CHECK(launch_pdl(layernorm_kernel<5>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 6: TAN_CHECK(launch_pdl(layernorm_kernel<6>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    case 7: TAN_CHECK(launch_pdl(layernorm_kernel<7>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
+    default: TAN_CHECK(launch_pdl(layernorm_kernel<8>, dim3(blocks), dim3(warps * 32), 0, st, 1, a)); break;
   }
   TAN_CUDA(cudaGetLastError());
   return TAN_OK;

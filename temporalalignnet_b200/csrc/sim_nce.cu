@@ -187,6 +187,8 @@ __global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, c
   const int64_t nrow = 2 * c.R;
   const int64_t ncol = 2ll * c.g.S * c.g.C;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nrow + ncol; i += stride) {
     if (i < nrow) {
       const int64_t w = i / c.R, r = i % c.R;
@@ -253,6 +255,8 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, float* __re
   const int pos_c0 = bg * c.g.N, pos_c1 = pos_c0 + c.g.N;
   const bool aligned = (c.g.C % 8) == 0 && col0 + 8 <= c.g.C;
   const bool slab_has_pos = slab * kNceCols < pos_c1 && (slab + 1) * kNceCols > pos_c0;   // CTA-uniform
+  pdl_launch_dependents();
+  pdl_wait();
 
   uint32_t okbits = 0;
   float st[8], en[8];
@@ -366,6 +370,8 @@ __global__ void nce_reduce_kernel(const float* __restrict__ row_sums, int64_t R,
                                   int64_t SC, int do_rows, int do_cols, double* __restrict__ out) {
   // fp64 accumulation: the cross-block atomic order then only perturbs bits far below fp32 epsilon
   double acc[4] = {0., 0., 0., 0.};
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t i0 = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (do_rows) {
@@ -501,9 +507,8 @@ extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfe
   const int64_t total = 2 * c.R + 2ll * g->S * g->C;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  sim_reduce_partials_kernel<<<blocks, 256, 0, st>>>(row_part, col_part, c, row_sums, col_sums);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
+  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c, row_sums,
+                    col_sums);
 }
 
 extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const tan_sim_geom* g,
@@ -529,16 +534,14 @@ extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const 
   if (g->B_loc * g->S > 65535) return set_error(TAN_ERR_SHAPE, "tan_nce_from_logits: B_loc*S > 65535");
   dim3 grid(c.n_tiles, g->B_loc * g->S);
   if (logits_is_f32)
-    nce_from_logits_kernel<true><<<grid, kNceWarps * 32, 0, st>>>(logits, c, row_part, col_part);
+    TAN_CHECK(launch_pdl(nce_from_logits_kernel<true>, grid, dim3(kNceWarps * 32), 0, st, 1, logits, c, row_part, col_part));
   else
-    nce_from_logits_kernel<false><<<grid, kNceWarps * 32, 0, st>>>(logits, c, row_part, col_part);
-  TAN_CUDA(cudaGetLastError());
+    TAN_CHECK(launch_pdl(nce_from_logits_kernel<false>, grid, dim3(kNceWarps * 32), 0, st, 1, logits, c, row_part, col_part));
   const int64_t total = 2 * c.R + 2ll * g->S * g->C;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  sim_reduce_partials_kernel<<<blocks, 256, 0, st>>>(row_part, col_part, c, row_sums, col_sums);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
+  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c, row_sums,
+                    col_sums);
 }
 
 extern "C" int tan_nce_reduce(const float* row_sums, int64_t R, const float* col_sums, int64_t SC, int do_rows,
@@ -550,8 +553,6 @@ extern "C" int tan_nce_reduce(const float* row_sums, int64_t R, const float* col
   int blocks = static_cast<int>((n + 255) / 256);
   if (blocks < 1) blocks = 1;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-  nce_reduce_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_sums, R, col_sums, SC, do_rows,
-                                                                            do_cols, out);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
+  return launch_pdl(nce_reduce_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, row_sums, R,
+                    col_sums, SC, do_rows, do_cols, out);
 }

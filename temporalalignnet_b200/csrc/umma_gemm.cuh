@@ -58,15 +58,6 @@ struct TileCoord {
   int b_row;   // TMA row coordinate of the (full, BN-row) B tile; identical for all CTAs of a cluster
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0,
                                                   int crd1, uint16_t mask) {
   asm volatile(
@@ -155,6 +146,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CS > 1) cluster_sync_all();                 // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) trace_evt(tr, 2);
 
   if (warp == 0) {
@@ -267,13 +260,15 @@ int launch_umma_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Epi& 
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CS;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   // persistent grid = the number of clusters that can be co-resident (GPC sizes may strand a few SMs)
   static int max_clusters = 0;
   if (max_clusters == 0) {
