@@ -98,6 +98,24 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return make_tmap_2d(out, base, 2, rows, cols, ld, box_rows);
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t segs, uint64_t rows, uint64_t cols,
+                      uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return set_error(TAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 2) % 16 != 0)
+    return set_error(TAN_ERR_SHAPE, "TMA operand needs a 16-byte aligned base and row pitch");
+  if (box_rows == 0 || box_rows > 256) return set_error(TAN_ERR_SHAPE, "TMA box must have 1..256 rows");
+  const cuuint64_t gdim[3] = {cols, rows, segs};
+  const cuuint64_t gstride[2] = {cols * 2, rows * cols * 2};
+  const cuuint32_t box[3] = {64, box_rows, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TAN_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", int(r));
+  return TAN_OK;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

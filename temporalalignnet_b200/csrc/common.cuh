@@ -29,6 +29,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows);
 
+// 3-D row-major bf16 tensor [segs, rows, cols] (contiguous), box [1, box_rows, 64], 128-byte swizzle.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t segs, uint64_t rows, uint64_t cols,
+                      uint32_t box_rows);
+
 #define TAN_CHECK(expr)                         \
   do {                                          \
     int _e = (expr);                            \
@@ -230,6 +234,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+// 3-D variant (crd2 = outermost): the box is clipped against every tensor dimension, so a [1 x 32 x 64] box
+// never spills from one (clip, stage) segment into the next.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int crd0, int crd1,
+                                             int crd2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1), "r"(crd2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -13,7 +13,7 @@
 // partial sums from different tiles / ranks add directly:  e = exp((cos - 1)/0.07) in (0, 1].
 #include <cstdlib>
 
-#include "umma_gemm.cuh"
+#include "umma_gemm2.cuh"
 
 namespace tanb {
 
@@ -47,69 +47,76 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN>
-struct SimEpi {
-  // per-quarter column partials: [4 quarters][2 (all,pos)][BN]
-  static constexpr int kExtraSmem = 4 * 2 * BN * 4;
+// Epilogue of the CTA-pair GEMM (umma_gemm2.cuh) for the similarity matrix.  Pair tile = 256 frames of one
+// (clip, stage) segment x 256 text columns; this CTA owns 128 of the frames.  Epilogue warp (quarter, half)
+// turns 32 frames x 128 columns of cosines into exp-sums: per frame (thread-local over its columns, one
+// partial per (column tile, half)) and per column (transposing butterfly over the warp's 32 frames, then a
+// fixed-order combine of the four quarters through shared memory: deterministic, no atomics).
+// Optional bf16 logits: staged as [32 x 64] boxes (128-byte swizzle) and written with TMA stores.
+struct SimEpi2 {
+  static constexpr int kStages = 4;
+  static constexpr int kWarpScratch = 2 * 4096 + 1024;    // two logits boxes + this warp's share of the column partials
   struct State {};
-  SimCommon c;
-  int cs;                  // cluster size; (B_loc * seg_tiles) % cs == 0 so a cluster never straddles a stage
+  SimCommon c;             // seg_tiles = ceil(T / 256) PAIR tiles per segment; m_tiles counts 128-row CTA tiles
+  int pair_m_tiles;        // B_loc * S * seg_tiles
   int64_t b_stage_rows;    // rows of B per stage in the B tensor map (0 for the dual encoder)
-  bf16* logits;            // optional [R, C]
-  float* row_part;         // [2][n_tiles][R]
+  int store_logits;        // 0 none, 1 TMA boxes through tmOut (3-D map [segment][T][C], needs C % 8 == 0), 2 direct
+  bf16* logits;            // mode 2
+  float* row_part;         // [2][2 * n_tiles][R]
   float* col_part;         // [2][m_tiles][C]
 
-  __device__ __forceinline__ int num_ctiles() const { return (c.m_tiles / cs) * c.n_tiles; }
-  // Cluster tiles walk the row tiles STAGE-major (s, b, i) so that the cs row tiles of a cluster share
-  // the stage (= the same B tile); the returned tile id is in the natural (b, s, i) numbering.
-  __device__ __forceinline__ int tile_id(int ct, int rank) const {
-    const int tn = ct % c.n_tiles;
-    const int q = (ct / c.n_tiles) * cs + rank;                 // index in (s, b, i) order
-    const int per_stage = c.g.B_loc * c.seg_tiles;
-    const int s = q / per_stage, rem = q % per_stage;
-    const int b = rem / c.seg_tiles, i = rem % c.seg_tiles;
-    const int tm = (b * c.g.S + s) * c.seg_tiles + i;
-    return tm * c.n_tiles + tn;
-  }
-  __device__ __forceinline__ TileCoord coord(int tile) const {
-    const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
-    const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
-    TileCoord tc;
-    tc.a_row = seg * c.g.T + i * kGemmBM;
-    tc.b_row = static_cast<int>((seg % c.g.S) * b_stage_rows) + tn * BN;
-    return tc;
+  __device__ __forceinline__ int num_tiles() const { return pair_m_tiles * c.n_tiles; }
+  // column tiles fastest: the pair tiles in flight share their A rows and sweep B
+  __device__ __forceinline__ PairTile coord(int tile) const {
+    const int pm = tile / c.n_tiles, tn = tile % c.n_tiles;
+    const int seg = pm / c.seg_tiles, i = pm % c.seg_tiles;
+    PairTile pt;
+    pt.a_row = seg * c.g.T + i * 256;
+    pt.b_row = static_cast<int>((seg % c.g.S) * b_stage_rows) + tn * kG2BN;
+    return pt;
   }
 
-  __device__ __forceinline__ void init(uint8_t*) const {}
-  __device__ __forceinline__ void pre(int, int, int, uint8_t*, State&) const {}
+  __device__ __forceinline__ void pre(int, uint32_t, int, int, uint8_t*, float*, uint64_t*, uint32_t,
+                                      const CUtensorMap*, const CUtensorMap*, State&) const {}
 
-  __device__ __forceinline__ void run(int tile, uint32_t tmem_acc, int quarter, int lane, uint8_t* scratch,
+  __device__ __forceinline__ void run(int tile, uint32_t rank, uint32_t tmem_acc, int ew, int lane, uint8_t* ws,
+                                      float*, uint64_t*, uint32_t, const CUtensorMap* tmOut, const CUtensorMap*,
                                       State&) const {
-    const int tm = tile / c.n_tiles, tn = tile % c.n_tiles;
-    const int seg = tm / c.seg_tiles, i = tm % c.seg_tiles;
-    const int t = i * kGemmBM + quarter * 32 + lane;          // frame index of this thread's row
+    const int quarter = ew & 3, half = ew >> 2;
+    const int pm = tile / c.n_tiles, tn = tile % c.n_tiles;
+    const int seg = pm / c.seg_tiles, i = pm % c.seg_tiles;
+    const int t = i * 256 + static_cast<int>(rank) * 128 + quarter * 32 + lane;   // frame index of this thread's row
     const bool row_ok = t < c.g.T;
     const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
     const int bg = c.g.b_off + seg / c.g.S;                   // global clip of this row
     const int pos_c0 = bg * c.g.N, pos_c1 = pos_c0 + c.g.N;   // the only columns that can be positive
     const float tf = static_cast<float>(t);
-    const int n0 = tn * BN;
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* scol = reinterpret_cast<float*>(scratch) + quarter * 2 * BN;
+    const int n0 = tn * kG2BN + half * 128;                   // first column of this warp
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + half * 128;
+    // column partials: [quarter][2 (all, pos)][256] floats spread over the eight 1 KB warp tails
+    uint8_t* sbase = ws - ew * kWarpScratch;
+    auto scol = [&](int q, int which, int col) -> float& {
+      const int idx = (q * 2 + which) * 256 + col;            // 0 .. 2047
+      return *reinterpret_cast<float*>(sbase + (idx >> 8) * kWarpScratch + 2 * 4096 + (idx & 255) * 4);
+    };
+    const bool all_rows = __all_sync(0xffffffffu, row_ok);
     float row_all = 0.f, row_pos = 0.f;
-    const bool vec_store = (c.g.C % 8) == 0;
 
-#pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
+    if (store_logits == 1 && lane == 0) tma_store_wait_read<0>();  // previous tile's boxes have been read out
+    uint32_t raw[2][32];
+    tmem_ld_32x32(taddr, raw[0]);
+    if (store_logits == 1) __syncwarp();
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
       const int col0 = n0 + ch * 32;
-      if (col0 >= c.g.C) {                                    // warp-uniform: nothing but zeros left
-        scol[ch * 32 + lane] = 0.f;
-        scol[BN + ch * 32 + lane] = 0.f;
+      tmem_ld_wait();
+      if (ch + 1 < 4) tmem_ld_32x32(taddr + (ch + 1) * 32, raw[(ch + 1) & 1]);
+      const uint32_t(&rc)[32] = raw[ch & 1];
+      if (col0 >= c.g.C) {                                    // warp-uniform: nothing but zero padding left
+        scol(quarter, 0, half * 128 + ch * 32 + lane) = 0.f;
+        scol(quarter, 1, half * 128 + ch * 32 + lane) = 0.f;
         continue;
       }
-      uint32_t raw[32];
-      tmem_ld_32x32(taddr + ch * 32, raw);
-      tmem_ld_wait();
       // lane j looks up column col0 + j once; shuffled to everyone below
       const int mycol = col0 + lane;
       const bool my_ok = mycol < c.g.C && c.col_valid[mycol] != 0;
@@ -120,33 +127,43 @@ struct SimEpi {
         my_start = c.start[mycol];
         my_end = c.end[mycol];                                           // else start >= end: never positive
       }
-      if (logits != nullptr && row_ok) {
+      if (store_logits == 2 && row_ok) {                        // generic tail path (C % 8 != 0): per-thread stores
         bf16* dst = logits + r * c.g.C + col0;
-        if (vec_store && col0 + 32 <= c.g.C) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(raw[8 * j + 0]), __uint_as_float(raw[8 * j + 1]));
-            u.y = pack_bf16x2(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3]));
-            u.z = pack_bf16x2(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5]));
-            u.w = pack_bf16x2(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7]));
-            reinterpret_cast<uint4*>(dst)[j] = u;
-          }
-        } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < c.g.C) dst[j] = __float2bfloat16_rn(__uint_as_float(rc[j]));
+      }
+      if (store_logits == 1) {
+        // 32 columns = 64 bytes = chunks [4 * (ch & 1), +4) of this row of the [32 x 64] bf16 box
+        uint8_t* buf = ws + (ch >> 1) * 4096;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < c.g.C) dst[j] = __float2bfloat16_rn(__uint_as_float(raw[j]));
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(rc[8 * j + 0]), __uint_as_float(rc[8 * j + 1]));
+          u.y = pack_bf16x2(__uint_as_float(rc[8 * j + 2]), __uint_as_float(rc[8 * j + 3]));
+          u.z = pack_bf16x2(__uint_as_float(rc[8 * j + 4]), __uint_as_float(rc[8 * j + 5]));
+          u.w = pack_bf16x2(__uint_as_float(rc[8 * j + 6]), __uint_as_float(rc[8 * j + 7]));
+          *reinterpret_cast<uint4*>(buf + lane * 128 + (((4 * (ch & 1) + j) ^ (lane & 7)) << 4)) = u;
         }
       }
       float e[32];
+      if (all_rows && okmask == 0xffffffffu) {                 // common case: no masking at all
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = fast_exp2(fmaf(__uint_as_float(raw[j]), kExpScale, -kExpScale));
-        e[j] = (row_ok && ((okmask >> j) & 1u)) ? x : 0.f;
-        row_all += e[j];
+        for (int j = 0; j < 32; ++j) {
+          e[j] = fast_exp2(fmaf(__uint_as_float(rc[j]), kExpScale, -kExpScale));
+          row_all += e[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = fast_exp2(fmaf(__uint_as_float(rc[j]), kExpScale, -kExpScale));
+          e[j] = (row_ok && ((okmask >> j) & 1u)) ? x : 0.f;
+          row_all += e[j];
+        }
       }
-      float pe[32];
+      float cpos = 0.f;
       if (chunk_has_pos) {
+        float pe[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float s = __shfl_sync(0xffffffffu, my_start, j);
@@ -154,36 +171,49 @@ struct SimEpi {
           pe[j] = (s <= tf && tf < en) ? e[j] : 0.f;
           row_pos += pe[j];
         }
+        cpos = warp_column_sums(pe, lane);
       }
       const float call = warp_column_sums(e, lane);
-      scol[ch * 32 + lane] = call;
-      float cpos = 0.f;
-      if (chunk_has_pos) cpos = warp_column_sums(pe, lane);
-      scol[BN + ch * 32 + lane] = cpos;
+      scol(quarter, 0, half * 128 + ch * 32 + lane) = call;
+      scol(quarter, 1, half * 128 + ch * 32 + lane) = cpos;
+    }
+    if (store_logits == 1) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      const int t0 = i * 256 + static_cast<int>(rank) * 128 + quarter * 32;    // the box is clipped at T and C
+      if (lane == 0 && t0 < c.g.T) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+          if (n0 + 64 * p < c.g.C) tma_store_3d(tmOut, ws + p * 4096, n0 + 64 * p, t0, seg);
+        tma_store_commit();
+      }
     }
     if (row_ok) {
-      row_part[(static_cast<int64_t>(0) * c.n_tiles + tn) * c.R + r] = row_all;
-      row_part[(static_cast<int64_t>(1) * c.n_tiles + tn) * c.R + r] = row_pos;
+      const int64_t part = static_cast<int64_t>(tn) * 2 + half;
+      row_part[(static_cast<int64_t>(0) * 2 * c.n_tiles + part) * c.R + r] = row_all;
+      row_part[(static_cast<int64_t>(1) * 2 * c.n_tiles + part) * c.R + r] = row_pos;
     }
-    // combine the four quarters in a fixed order (deterministic) and publish this tile's column partials
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const float* s0 = reinterpret_cast<const float*>(scratch);
-    const int tid = quarter * 32 + lane;
-    for (int j = tid; j < 2 * BN; j += kEpiThreads) {
-      const int which = j / BN, cj = j % BN;
-      const int col = n0 + cj;
+    // combine the four quarters in a fixed order (deterministic) and publish this CTA tile's column partials
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int tm = (seg * c.seg_tiles + i) * 2 + static_cast<int>(rank);     // 128-row CTA tile index
+    const int tid = ew * 32 + lane;
+    for (int j = tid; j < 2 * 256; j += 256) {
+      const int which = j >> 8, cj = j & 255;
+      const int col = tn * kG2BN + cj;
       if (col < c.g.C) {
-        const float sum = ((s0[0 * 2 * BN + j] + s0[1 * 2 * BN + j]) + s0[2 * 2 * BN + j]) + s0[3 * 2 * BN + j];
+        const float sum = ((scol(0, which, cj) + scol(1, which, cj)) + scol(2, which, cj)) + scol(3, which, cj);
         col_part[(static_cast<int64_t>(which) * c.m_tiles + tm) * c.g.C + col] = sum;
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch is reused by the next tile
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // scratch is reused by the next tile
   }
 };
 
-// row_sums[w][r] = sum_tn row_part[w][tn][r];  col_sums[w][s][c] = sum over the m-tiles of stage s.
+// row_sums[w][r] = sum_p row_part[w][p][r] (p < row_parts);  col_sums[w][s][c] = sum over the m-tiles of stage s
+// (seg_parts consecutive m-tiles per (clip, stage) segment).
 __global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, const float* __restrict__ col_part,
-                                           SimCommon c, float* __restrict__ row_sums, float* __restrict__ col_sums) {
+                                           SimCommon c, int row_parts, int seg_parts, float* __restrict__ row_sums,
+                                           float* __restrict__ col_sums) {
   const int64_t nrow = 2 * c.R;
   const int64_t ncol = 2ll * c.g.S * c.g.C;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -193,7 +223,7 @@ __global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, c
     if (i < nrow) {
       const int64_t w = i / c.R, r = i % c.R;
       float s = 0.f;
-      for (int tn = 0; tn < c.n_tiles; ++tn) s += row_part[(w * c.n_tiles + tn) * c.R + r];
+      for (int p = 0; p < row_parts; ++p) s += row_part[(w * row_parts + p) * c.R + r];
       row_sums[i] = s;
     } else {
       const int64_t k = i - nrow;
@@ -203,8 +233,8 @@ __global__ void sim_reduce_partials_kernel(const float* __restrict__ row_part, c
       float s = 0.f;
       for (int b = 0; b < c.g.B_loc; ++b) {
         const int seg = b * c.g.S + s_idx;
-        for (int t = 0; t < c.seg_tiles; ++t)
-          s += col_part[(w * c.m_tiles + (seg * c.seg_tiles + t)) * c.g.C + col];
+        for (int t = 0; t < seg_parts; ++t)
+          s += col_part[(w * c.m_tiles + (seg * seg_parts + t)) * c.g.C + col];
       }
       col_sums[k] = s;
     }
@@ -408,7 +438,7 @@ __global__ void nce_reduce_kernel(const float* __restrict__ row_sums, int64_t R,
 }
 
 static int fill_common(SimCommon* c, const tan_sim_geom* g, const float* start, const float* end,
-                       const uint8_t* col_valid, int bn) {
+                       const uint8_t* col_valid) {
   if (g == nullptr || start == nullptr || end == nullptr || col_valid == nullptr)
     return set_error(TAN_ERR_ARG, "sim/nce: null geometry or mask pointer");
   if (g->B_loc <= 0 || g->S <= 0 || g->T <= 0 || g->C <= 0 || g->N <= 0 || g->d <= 0 || g->b_off < 0 ||
@@ -419,20 +449,16 @@ static int fill_common(SimCommon* c, const tan_sim_geom* g, const float* start, 
   c->start = start;
   c->end = end;
   c->col_valid = col_valid;
-  c->seg_tiles = (g->T + kGemmBM - 1) / kGemmBM;
-  c->m_tiles = g->B_loc * g->S * c->seg_tiles;
-  c->n_tiles = (g->C + bn - 1) / bn;
+  c->seg_tiles = (g->T + 255) / 256;                       // pair tiles (256 frames) per segment
+  c->m_tiles = g->B_loc * g->S * c->seg_tiles * 2;         // 128-row CTA tiles
+  c->n_tiles = (g->C + 255) / 256;                         // 256-column tiles / slabs
   c->R = static_cast<int64_t>(g->B_loc) * g->S * g->T;
   return TAN_OK;
 }
 
-static int pick_bn(const tan_sim_geom* g) {
-  if (g->C > 128) return 256;
-  if (g->C > 64) return 128;
-  return 64;
-}
-
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static size_t row_part_bytes(const SimCommon& c) { return align256(2 * 2 * static_cast<size_t>(c.n_tiles) * c.R * 4); }
 
 }  // namespace tanb
 
@@ -440,13 +466,12 @@ using namespace tanb;
 
 extern "C" size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g) {
   if (g == nullptr || g->B_loc <= 0 || g->S <= 0 || g->T <= 0 || g->C <= 0) return 0;
-  // sized for the smallest tile width either producer may pick (64 for the GEMM, 256-col slabs for
-  // the streaming kernel) so one query covers both entry points
+  // one query covers both producers: row partials [2][2 * ceil(C/256)][R] (the streaming kernel uses half of
+  // them), column partials [2][B_loc * S * 2 * ceil(T/256)][C] (the streaming kernel uses one per segment)
   const int64_t R = static_cast<int64_t>(g->B_loc) * g->S * g->T;
-  const int64_t n_tiles = (g->C + 63) / 64;
-  const int64_t seg_tiles = (g->T + kGemmBM - 1) / kGemmBM;
-  const int64_t m_tiles = static_cast<int64_t>(g->B_loc) * g->S * seg_tiles;
-  return align256(2 * n_tiles * R * 4) + align256(2 * m_tiles * g->C * 4);
+  const int64_t n_tiles = (g->C + 255) / 256;
+  const int64_t m_tiles = static_cast<int64_t>(g->B_loc) * g->S * ((g->T + 255) / 256) * 2;
+  return align256(2 * 2 * n_tiles * R * 4) + align256(2 * m_tiles * g->C * 4);
 }
 
 extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfeat_stage_stride,
@@ -457,58 +482,44 @@ extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfe
   if (vfeat == nullptr || tfeat == nullptr || row_sums == nullptr || col_sums == nullptr)
     return set_error(TAN_ERR_ARG, "tan_sim_nce_fwd: null pointer");
   if (g == nullptr) return set_error(TAN_ERR_ARG, "tan_sim_nce_fwd: null geometry");
-  const int bn = pick_bn(g);
   SimCommon c;
-  TAN_CHECK(fill_common(&c, g, start, end, col_valid, bn));
-  if (g->d % kGemmBK != 0) return set_error(TAN_ERR_SHAPE, "tan_sim_nce_fwd: d %% 64 != 0 (d=%d)", g->d);
+  TAN_CHECK(fill_common(&c, g, start, end, col_valid));
+  if (g->d % kG2BK != 0) return set_error(TAN_ERR_SHAPE, "tan_sim_nce_fwd: d %% 64 != 0 (d=%d)", g->d);
   if (tfeat_stage_stride != 0 && tfeat_stage_stride != static_cast<int64_t>(g->C) * g->d)
     return set_error(TAN_ERR_SHAPE, "tan_sim_nce_fwd: tfeat_stage_stride must be 0 or C*d");
   if (workspace == nullptr || workspace_bytes < tan_sim_nce_workspace_bytes(g))
     return set_error(TAN_ERR_WORKSPACE, "tan_sim_nce_fwd: workspace too small (%zu < %zu)", workspace_bytes,
                      tan_sim_nce_workspace_bytes(g));
   float* row_part = static_cast<float*>(workspace);
-  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
-                                             align256(2 * static_cast<size_t>(c.n_tiles) * c.R * 4));
+  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + row_part_bytes(c));
   const int64_t b_rows = tfeat_stage_stride == 0 ? g->C : static_cast<int64_t>(g->S) * g->C;
-  // cluster size along M (B-tile multicast): the row tiles of one stage must split evenly
-  int cs = 2;
-  if (const char* e = getenv("TAN_SIM_CS")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) cs = v;
+  CUtensorMap tmA, tmB, tmOut;
+  TAN_CHECK(make_tmap_2d(&tmA, vfeat, 2, c.R, g->d, g->d, kG2BM));
+  TAN_CHECK(make_tmap_2d(&tmB, tfeat, 2, b_rows, g->d, g->d, kG2BN / 2));
+  SimEpi2 e;
+  e.c = c;
+  e.pair_m_tiles = g->B_loc * g->S * c.seg_tiles;
+  e.b_stage_rows = tfeat_stage_stride == 0 ? 0 : g->C;
+  e.logits = static_cast<bf16*>(logits_out);
+  e.store_logits = 0;
+  tmOut = tmA;
+  if (logits_out != nullptr) {
+    if (g->C % 8 == 0 && (reinterpret_cast<uintptr_t>(logits_out) & 15) == 0) {
+      e.store_logits = 1;
+      TAN_CHECK(make_tmap_3d_bf16(&tmOut, logits_out, static_cast<uint64_t>(g->B_loc) * g->S, g->T, g->C, 32));
+    } else {
+      e.store_logits = 2;
+    }
   }
-  while (cs > 1 && (g->B_loc * c.seg_tiles) % cs != 0) cs >>= 1;
-  CUtensorMap tmA, tmB;
-  TAN_CHECK(make_tmap_2d_bf16(&tmA, vfeat, c.R, g->d, g->d, kGemmBM, kGemmBK));
-  TAN_CHECK(make_tmap_2d_bf16(&tmB, tfeat, b_rows, g->d, g->d, bn / cs, kGemmBK));
+  e.row_part = row_part;
+  e.col_part = col_part;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define TAN_LAUNCH_SIM(BN_, CS_)                                                                      \
-  {                                                                                                   \
-    SimEpi<BN_> e;                                                                                    \
-    e.c = c;                                                                                          \
-    e.cs = CS_;                                                                                       \
-    e.b_stage_rows = tfeat_stage_stride == 0 ? 0 : g->C;                                              \
-    e.logits = static_cast<bf16*>(logits_out);                                                        \
-    e.row_part = row_part;                                                                            \
-    e.col_part = col_part;                                                                            \
-    TAN_CHECK((launch_umma_gemm<BN_, CS_, SimEpi<BN_>>(tmA, tmB, e, (c.m_tiles / CS_) * c.n_tiles,    \
-                                                        g->d / kGemmBK, st)));                        \
-  }
-#define TAN_LAUNCH_SIM_CS(BN_)                  \
-  {                                             \
-    if (cs == 4) TAN_LAUNCH_SIM(BN_, 4)         \
-    else if (cs == 2) TAN_LAUNCH_SIM(BN_, 2)    \
-    else TAN_LAUNCH_SIM(BN_, 1)                 \
-  }
-  if (bn == 256) TAN_LAUNCH_SIM_CS(256)
-  else if (bn == 128) TAN_LAUNCH_SIM_CS(128)
-  else TAN_LAUNCH_SIM_CS(64)
-#undef TAN_LAUNCH_SIM_CS
-#undef TAN_LAUNCH_SIM
+  TAN_CHECK(launch_umma_gemm2<SimEpi2>(tmA, tmB, tmOut, tmOut, e, e.pair_m_tiles * c.n_tiles, g->d / kG2BK, st));
   const int64_t total = 2 * c.R + 2ll * g->S * g->C;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c, row_sums,
-                    col_sums);
+  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c,
+                    2 * c.n_tiles, 2 * c.seg_tiles, row_sums, col_sums);
 }
 
 extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const tan_sim_geom* g,
@@ -520,7 +531,7 @@ extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const 
     return set_error(TAN_ERR_ARG, "tan_nce_from_logits: null pointer");
   if (g == nullptr) return set_error(TAN_ERR_ARG, "tan_nce_from_logits: null geometry");
   SimCommon c;
-  TAN_CHECK(fill_common(&c, g, start, end, col_valid, kNceCols));
+  TAN_CHECK(fill_common(&c, g, start, end, col_valid));
   if (workspace == nullptr || workspace_bytes < tan_sim_nce_workspace_bytes(g))
     return set_error(TAN_ERR_WORKSPACE, "tan_nce_from_logits: workspace too small (%zu < %zu)", workspace_bytes,
                      tan_sim_nce_workspace_bytes(g));
@@ -528,8 +539,7 @@ extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const 
   c.seg_tiles = 1;
   c.m_tiles = g->B_loc * g->S;
   float* row_part = static_cast<float*>(workspace);
-  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
-                                             align256(2 * static_cast<size_t>(c.n_tiles) * c.R * 4));
+  float* col_part = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + row_part_bytes(c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (g->B_loc * g->S > 65535) return set_error(TAN_ERR_SHAPE, "tan_nce_from_logits: B_loc*S > 65535");
   dim3 grid(c.n_tiles, g->B_loc * g->S);
@@ -540,8 +550,8 @@ extern "C" int tan_nce_from_logits(const void* logits, int logits_is_f32, const 
   const int64_t total = 2 * c.R + 2ll * g->S * g->C;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c, row_sums,
-                    col_sums);
+  return launch_pdl(sim_reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, 1, row_part, col_part, c, c.n_tiles,
+                    1, row_sums, col_sums);
 }
 
 extern "C" int tan_nce_reduce(const float* row_sums, int64_t R, const float* col_sums, int64_t SC, int do_rows,

@@ -15,6 +15,38 @@ from ._lib import LnArgs, SimGeom, check, lib
 
 _launches = 0          # kernels launched through this module (bench.py's `gpu_launches` claim)
 _prof = None           # when a list: (kernel, work, start_event, end_event) per call (bench.py roofline pass)
+_only = None           # measurement aid: when set, only this kernel class is launched (see `only_class`)
+_work = {}             # per-class (algorithmic work, launches) accumulated while `_only` is set
+
+
+class only_class:
+    """Context manager for bench.py's per-kernel timing: inside it every C-ABI wrapper except `name`
+    returns without launching, so a CUDA graph captured around one step holds exactly that kernel
+    class's launches (in step order, on the step's real buffers).  Kernels do not branch on data
+    values, so skipping the producers changes no launch.  Not used on the product path."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        global _only
+        _only = self.name
+        _work[self.name] = [0.0, 0]
+        return _work[self.name]
+
+    def __exit__(self, *a):
+        global _only
+        _only = None
+
+
+def _skip(name: str, work: float = 0.0, n: int = 1) -> bool:
+    if _only is None:
+        return False
+    if _only == name:
+        _work[name][0] += work
+        _work[name][1] += n
+        return False
+    return True
 
 
 class profile:
@@ -72,6 +104,8 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     _need(x, torch.float32, "cast_bf16.in")
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if _skip("cast", float(x.numel())):
+        return out
     check(lib().tan_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "tan_cast_f32_to_bf16")
     _launches += 1
     return out
@@ -85,6 +119,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     global _launches
     M, K = a.shape
     N = w.shape[0]
+    if _skip("linear", 2.0 * M * N * K):
+        return
     with _timed("linear", 2.0 * M * N * K):
         check(lib().tan_linear_bf16(
             a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
@@ -104,6 +140,8 @@ def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=Non
     global _launches
     L_in = rows if L_in is None else L_in
     L_out = L_in if L_out is None else L_out
+    if _skip("layernorm", float(rows) * d):
+        return
     a = LnArgs(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, d, _ptr(gamma), _ptr(beta), _ptr(add), add_rows,
                L_in, L_out, l_off, _ptr(out_f32), _ptr(out_bf16), l_split, strideA, strideB,
                _ptr(rawA), _ptr(rawB), _ptr(nrmA_bf16), _ptr(nrmB_bf16), _ptr(nrmA_f32), _ptr(nrmB_f32))
@@ -116,6 +154,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kpm_u8: Optiona
               out: torch.Tensor, B: int, H: int, Lq: int, Lk: int) -> None:
     """tan_attention_bf16.  q/k/v/out are 2-D (possibly column-sliced) bf16 views [B*L, H*64]."""
     global _launches
+    if _skip("attention", 4.0 * B * H * Lq * Lk * 64):
+        return
     with _timed("attention", 4.0 * B * H * Lq * Lk * 64):
         check(lib().tan_attention_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
                                        v.stride(0), _ptr(kpm_u8), out.data_ptr(), out.stride(0), B, H, Lq, Lk,
@@ -134,6 +174,8 @@ def sim_workspace_bytes(g: SimGeom) -> int:
 def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride: int, g: SimGeom, start, end, col_valid, logits_out,
                 row_sums, col_sums, workspace) -> None:
     global _launches
+    if _skip("sim_nce_fwd", 2.0 * g.B_loc * g.S * g.T * g.C * g.d, 2):
+        return
     with _timed("sim_nce_fwd", 2.0 * g.B_loc * g.S * g.T * g.C * g.d):
         check(lib().tan_sim_nce_fwd(vfeat.data_ptr(), tfeat.data_ptr(), tfeat_stage_stride, C.byref(g),
                                     start.data_ptr(), end.data_ptr(), col_valid.data_ptr(), _ptr(logits_out),
@@ -147,6 +189,8 @@ def nce_from_logits(logits, g: SimGeom, start, end, col_valid, row_sums, col_sum
     is_f32 = int(logits.dtype == torch.float32)
     if not is_f32 and logits.dtype != torch.bfloat16:
         raise _lib.TanError(f"nce_from_logits: logits must be fp32 or bf16, got {logits.dtype}")
+    if _skip("nce_from_logits", float(logits.numel()) * logits.element_size(), 2):
+        return
     with _timed("nce_from_logits", float(logits.numel()) * logits.element_size()):
         check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), start.data_ptr(), end.data_ptr(),
                                         col_valid.data_ptr(), row_sums.data_ptr(), col_sums.data_ptr(),
@@ -159,6 +203,8 @@ def nce_reduce(row_sums, col_sums, out4_f64, do_rows=True, do_cols=True) -> None
     global _launches
     R = row_sums.numel() // 2 if row_sums is not None else 0
     SC = col_sums.numel() // 2 if col_sums is not None else 0
+    if _skip("nce_reduce", float(R + SC)):
+        return
     check(lib().tan_nce_reduce(_ptr(row_sums), R, _ptr(col_sums), SC, int(do_rows), int(do_cols),
                                out4_f64.data_ptr(), _stream()), "tan_nce_reduce")
     _launches += 1

@@ -36,12 +36,20 @@ class TanStepRunner:
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.shard = world_size > 1
+        # one GPU: the whole step (forward + loss) is one CUDA graph; several GPUs: the forward (no
+        # collectives) replays from the model's own graph cache and the loss (NCCL all-gather / all-reduce
+        # + a dozen launches) is enqueued eagerly behind it
+        # (capturing the NCCL collectives as well was measured at -3 % step time on 2 GPUs and hung at
+        # process-group teardown, so it is not offered)
         self.use_graph = use_graph and world_size == 1
+        self.use_model_graph = use_graph
         self.args = default_loss_args()
         sd = synth.make_state_dict(self.E, self.D, width=width, d_in=video_dim, seed=seed, perturb=False)
         self.model = TemporalAligner(self.E, self.D, random_pos_start=0, width=width, video_dim=video_dim)
         self.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         self.model = self.model.to(self.device)
+        if self.use_model_graph:
+            self.model.enable_cuda_graphs(True)
         self.batch = synth.make_batch(B_loc, T, self.N, d_in=video_dim, seed=seed, tag=f"rank{rank}")
         # pinned host copies (the e2e path starts here) and device-resident copies
         self.h_video = torch.from_numpy(self.batch["video"]).pin_memory()
@@ -94,6 +102,28 @@ class TanStepRunner:
             g.replay()
             torch.cuda.synchronize()
         return float(loss)
+
+    def class_graph(self, name: str):
+        """(graph, work, launches) holding ONLY the launches of kernel class `name` of one resident step
+        (ops.only_class).  bench.py replays it to get that kernel's average launch duration with CUDA
+        events alone -- per-launch event pairs on eagerly launched kernels also time the host's launch
+        preparation whenever the GPU runs dry."""
+        shard, self.shard = self.shard, False        # no collectives inside these measurement graphs
+        graphs_on, self.model._graphs_on = self.model._graphs_on, False
+        try:
+            with ops.only_class(name) as acc:
+                self._step_kernels()                 # eager dry run: allocations
+                torch.cuda.synchronize()
+                acc[0], acc[1] = 0.0, 0
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_kernels()
+        finally:
+            self.shard = shard
+            self.model._graphs_on = graphs_on
+        g.replay()
+        torch.cuda.synchronize()
+        return g, acc[0], acc[1]
 
     def step_resident(self) -> torch.Tensor:
         if self._graph is not None:

@@ -42,9 +42,18 @@ class _Bf16Cache:
             w = p.detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
-            ent = (p._version, p.data_ptr(), ops.cast_bf16(w))
+            # refresh IN PLACE when possible: captured CUDA graphs keep pointing at the same shadow
+            keep = ent[2] if (ent is not None and ent[2].shape == w.shape and ent[2].device == w.device) else None
+            ent = (p._version, p.data_ptr(), ops.cast_bf16(w, keep), p)
             self._c[key] = ent
         return ent[2]
+
+    def refresh(self) -> None:
+        """Re-cast every shadow whose parameter changed since it was made (called before a graph replay)."""
+        for ent in list(self._c.values()):
+            p = ent[3]
+            if ent[0] != p._version or ent[1] != p.data_ptr():
+                self.get(p)
 
 
 def _f32(p: torch.Tensor) -> torch.Tensor:
