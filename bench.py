@@ -325,7 +325,7 @@ def hbm_nce_roofline(runner, peaks, flush):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ops.nce_from_logits(dense, g, nce.start, nce.end, nce.col_valid, rs, cs, ws)
+        ops.nce_from_logits(dense, g, nce.posbits, nce.col_valid, rs, cs, ws)
         b.record()
         torch.cuda.synchronize()
         if i >= 3:

@@ -148,8 +148,7 @@ TAN_API int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int64_
  *   rows   r = (b * S + s) * T + t   for local clip b < B_loc, stage s < S, frame t < T
  *   cols   c = b' * N + n            for GLOBAL clip b' and sentence n;  C = B_glob * N
  *   z[r, c] = <vfeat[r], tfeat_s[c]> / 0.07                       (train/loss.py:65-67)
- *   positive(r, c) <=> b_off + b == b' and col_valid[c] and start[c] <= t < end[c]
- *                                                   (train/loss.py:26-41,:80-85)
+ *   positive(r, c) <=> b_off + b == b' and bit n of posbits[b][t] (below)
  * Sums use the fixed shift 1/0.07 (|cos| <= 1):  e = exp(z - 1/0.07). */
 typedef struct tan_sim_geom {
   int B_loc;   /* local clips (rows) */
@@ -161,7 +160,17 @@ typedef struct tan_sim_geom {
   int b_off;   /* global index of local clip 0 */
 } tan_sim_geom;
 
-/* Workspace (bytes) for tan_sim_nce_fwd partial sums. */
+/* Targets.  posbits [B_loc, T, W] uint32, W = ceil(N / 32): bit (n % 32) of word n / 32 of posbits[b][t] is
+ * set iff sentence n of LOCAL clip b is a positive of frame t.  Replaces the reference's float target tensor
+ * [B, T, B, N] (train/loss.py:80-85: block-diagonal, 2.1 GB at BASELINE config 3); bits of padded sentences
+ * and of n >= N must be 0.  The same format carries the interval targets of get_mask_from_time and the
+ * self-labelled targets of train/loss.py:88-229.
+ * tan_pos_from_time builds it from sentence times: bit = valid[b][n] && start[b][n] <= t < end[b][n]
+ * (train/loss.py:26-41; start/end [B, N] fp32, valid [B, N] uint8 or NULL = all valid). */
+TAN_API int tan_pos_from_time(const float* start, const float* end, const uint8_t* valid, int B, int T, int N,
+                      uint32_t* posbits, void* stream);
+
+/* Workspace (bytes) for the partial sums of tan_sim_nce_fwd / tan_nce_from_logits. */
 TAN_API size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g);
 
 /* Fused similarity GEMM + NCE statistics.
@@ -169,8 +178,9 @@ TAN_API size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g);
  *   tfeat bf16 L2-normalised text features: [C, d] shared by all stages (tfeat_stage_stride == 0,
  *         dual encoder, model/tan_model.py:118-119) or [S, C, d] (tfeat_stage_stride = C*d,
  *         joint encoder, :138-139);
- *   start/end [C] fp32 (padded sentences: start = T+100, end = -100, train/loss.py:32-39),
- *   col_valid [C] uint8 (1 = real sentence, i.e. ~text_padding_mask);
+ *   posbits as above; col_valid [C] uint8 (1 = real sentence, i.e. ~text_padding_mask, GLOBAL columns);
+ *   row_kill [B_loc, T] uint8 or NULL: 1 = the own-clip entries of this frame count as exp(-inf) (the
+ *         reference's in-place -6e4 fill of padded frames under --learn_agreement, train/loss.py:96-97);
  *   logits_out: NULL (fused mode, the matrix never leaves the SM) or bf16 [B_loc*S*T, C] (ld = C),
  *         written once = the reference's `logits_*` tensor [B,S,T,B,N] (cosines, NOT divided by 0.07);
  *   row_sums [2, B_loc*S*T] fp32: sum_c e (valid columns) and sum_{c positive} e;
@@ -179,26 +189,30 @@ TAN_API size_t tan_sim_nce_workspace_bytes(const tan_sim_geom* g);
  * Replaces torch.einsum at model/tan_model.py:118-119,:138-139 and the logits passes of
  * train/loss.py:65-67,:241-254,:261-271. */
 TAN_API int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfeat_stage_stride,
-                    const tan_sim_geom* g, const float* start, const float* end,
-                    const uint8_t* col_valid, void* logits_out, float* row_sums, float* col_sums,
+                    const tan_sim_geom* g, const uint32_t* posbits, const uint8_t* col_valid,
+                    const uint8_t* row_kill, void* logits_out, float* row_sums, float* col_sums,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same statistics from MATERIALISED logits (API-preserving mode: a caller hands get_loss a plain
- * `logits_*` tensor).  logits [B_loc*S*T, C] bf16 (logits_is_f32 == 0) or fp32, unscaled cosines.
- * HBM-bound: one coalesced pass, warp-shuffle row reductions, register column accumulators. */
+ * `logits_*` tensor).  logits [B_loc*S*T, C] bf16 (logits_is_f32 == 0) or fp32, unscaled cosines,
+ * 16-byte aligned.  HBM-bound: one coalesced pass, register column accumulators, butterfly row sums. */
 TAN_API int tan_nce_from_logits(const void* logits, int logits_is_f32, const tan_sim_geom* g,
-                        const float* start, const float* end, const uint8_t* col_valid,
+                        const uint32_t* posbits, const uint8_t* col_valid, const uint8_t* row_kill,
                         float* row_sums, float* col_sums, void* workspace, size_t workspace_bytes,
                         void* stream);
 
-/* Loss reduction (train/loss.py:248-256): from row_sums [2, R] and (globally reduced) col_sums
- * [2, S, C] accumulate
+/* Loss reduction (train/loss.py:248-256): from row_sums [2, R] (R = B_loc*S*T) and (globally reduced)
+ * col_sums [2, S*C] accumulate
  *   out[0] += sum over rows with a positive of log(all) - log(pos),  out[1] += their count,
  *   out[2] += sum over valid columns with a positive of log(all) - log(pos), out[3] += their count.
- * `out` [4] fp64 must be zeroed by the caller (fp64 so that the atomic accumulation order is
- * invisible at fp32 resolution); rows and columns may be reduced by separate calls / ranks. */
-TAN_API int tan_nce_reduce(const float* row_sums, int64_t R, const float* col_sums, int64_t SC,
-                   int do_rows, int do_cols, double* out, void* stream);
+ * Either side may be NULL (rows and columns may be reduced by separate calls / ranks).
+ * row_sel [B_loc, T] / col_sel [C] uint8 (or NULL) further restrict the rows / columns that count: the
+ * thresholded loss of train/loss.py:277-304 keeps the frames with a positive among the kept sentences and
+ * the kept sentences only.  `out` [4] fp64 must be zeroed by the caller (fp64 so that the atomic accumulation
+ * order is invisible at fp32 resolution). */
+TAN_API int tan_nce_reduce(const float* row_sums, int64_t R, int S, int T, const uint8_t* row_sel,
+                   const float* col_sums, int64_t SC, int C, const uint8_t* col_sel, double* out,
+                   void* stream);
 
 #ifdef __cplusplus
 }

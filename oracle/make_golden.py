@@ -148,6 +148,45 @@ def run_blocks():
     print("g_blocks", out["circulant_012"].tolist())
 
 
+# loss-only cases (every get_loss branch): name -> (B, S, T, N, pad_video_every, loss-arg overrides, use abs_text_pos)
+LOSS_CASES = {
+    "init": (4, 3, 32, 4, 0, dict(), False),
+    "init_pad": (4, 3, 32, 4, 2, dict(), False),
+    "agree_keep": (4, 3, 32, 4, 0, dict(learn_agreement=1), False),
+    "agree_i": (3, 3, 24, 5, 0, dict(learn_agreement=1, temporal_agreement_type="i"), False),
+    "agree_u": (3, 3, 24, 5, 0, dict(learn_agreement=1, temporal_agreement_type="u"), False),
+    "agree_keep_joint": (5, 4, 40, 6, 0, dict(learn_agreement=1, temporal_agreement_type="keep-joint"), False),
+    "cotrain_keep_pad": (4, 3, 32, 4, 2, dict(model="cotrain", learn_agreement=1), False),
+    "threshold": (6, 3, 64, 8, 0, dict(loss_threshold=0.5), False),
+    "head": (4, 3, 32, 4, 0, dict(use_alignability_head=1), True),
+    "all_init": (6, 3, 64, 8, 0, dict(learn_agreement=1, loss_threshold=0.5, use_alignability_head=1), True),
+    "all_cotrain_bce": (5, 4, 40, 6, 2, dict(model="cotrain", learn_agreement=1, loss_threshold=0.3,
+                                            use_alignability_head=1, optim_policy="bce"), True),
+    "n40": (3, 3, 48, 40, 0, dict(learn_agreement=1, loss_threshold=0.4, use_alignability_head=1), False),
+}
+
+
+def run_loss_cases():
+    """Reference get_loss (train/loss.py:55-422) on synthetic logits for every branch: agreement
+    self-labelling, threshold, alignability BCE, init / cotrain."""
+    tfm, tan, ref_loss = load_reference()
+    out = {}
+    for name, (B, S, T, N, pad, kw, use_pos) in LOSS_CASES.items():
+        case = synth.make_logit_case(B, S, T, N, tag=name, pad_video_every=pad)
+        batch = case["batch"]
+        logits = {k: torch.from_numpy(v.copy()) for k, v in case.items() if k not in ("batch", "abs_text_pos")}
+        vpm = torch.from_numpy(batch["video_padding_mask"]).float()
+        tpm = torch.from_numpy(batch["text_padding_mask"]).float()
+        atp = torch.from_numpy(case["abs_text_pos"]) if use_pos else None
+        res = ref_loss.get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]},
+                                torch.zeros(B, T, 1), torch.zeros(B, N, 1), vpm, tpm, logits, loss_args(**kw), atp)
+        for k, v in res.items():
+            out[f"{name}/{k}"] = np.array(float(v))
+        out[f"{name}/in_checksum"] = np.array(checksum(case["logits_dual"]) + checksum(case["logits_joint"]))
+        print(name, {k: round(float(v), 6) for k, v in res.items()})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_loss_full.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -162,6 +201,8 @@ def main():
         run_case(name, cfg)
     if not a.only or a.only == "g_blocks":
         run_blocks()
+    if not a.only or a.only == "g_loss_full":
+        run_loss_cases()
 
 
 if __name__ == "__main__":

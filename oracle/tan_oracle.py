@@ -304,3 +304,211 @@ def get_loss_init(logits_dual, logits_joint, start_list, end_list, text_padding_
     ld = nce_loss(_t(logits_dual), tgt, col_valid)
     lj = nce_loss(_t(logits_joint), tgt, col_valid)
     return {"loss": (ld + lj) / 2, "loss-dual": ld.detach(), "loss-joint": lj.detach()}
+
+
+# ------------------------------------------------------------------------------------------------
+# Loss, remaining branches: agreement self-labelling (L4), loss threshold + alignability BCE (L5)
+# ------------------------------------------------------------------------------------------------
+
+def quantile_linear(x, q: float):
+    """torch.quantile(x, q) (default 'linear' interpolation) on a 1-D tensor, restated:
+    sort, position q*(n-1), linear blend of the two neighbours."""
+    xs, _ = torch.sort(x.float().reshape(-1))
+    n = xs.numel()
+    pos = q * (n - 1)
+    lo = int(math.floor(pos))
+    hi = min(lo + 1, n - 1)
+    return xs[lo] + (xs[hi] - xs[lo]) * (pos - lo)
+
+
+def own_clip_block(z, video_padding_mask=None, text_padding_mask=None):
+    """z [B,S,T,B,N] -> its own-clip blocks [B,S,T,N] (torch.diagonal(dim1=0, dim2=3), train/loss.py:92-95)
+    with -6e4 on padded frames / padded sentences (:96-100)."""
+    B = z.shape[0]
+    blk = torch.stack([z[b, :, :, b, :] for b in range(B)])                   # [B,S,T,N]
+    if video_padding_mask is not None:
+        blk = blk.masked_fill(video_padding_mask[:, None, :, None], -6e4)
+    if text_padding_mask is not None:
+        blk = blk.masked_fill(text_padding_mask[:, None, None, :], -6e4)
+    return blk
+
+
+def best_window(q_bn, z_bn, dur: int):
+    """One sentence of the self-labelling scan (train/loss.py:111-145), without the [T,T] circulant.
+    q_bn [T]: the sentence's probability over time; z_bn [T]: its last-stage logits; dur: window length.
+    Window i covers frames [i, i+dur) for 0 <= i <= T-dur, never frames 0 and T-1 (:127-128); its score is
+    the MEAN of q over the frames it keeps.  Returns (score, window mask [T] bool, mean logit in the window);
+    the first best window wins ties (torch.max)."""
+    T = q_bn.shape[0]
+    best, best_i = torch.tensor(0.0), 0          # invalid windows score 0 and lose to any real one
+    scores = torch.zeros(T)
+    if dur >= 1:
+        for i in range(0, T - dur + 1):
+            lo, hi = max(i, 1), min(i + dur, T - 1)
+            if hi > lo:
+                scores[i] = (q_bn[lo:hi] * (1.0 / float(hi - lo))).sum()    # the reference's operation order (:133-134)
+    best, best_i = scores.max(0)
+    best_i = int(best_i)
+    win = torch.zeros(T, dtype=torch.bool)
+    mean_logit = torch.tensor(0.0)
+    if dur >= 1 and best_i <= T - dur:
+        lo, hi = max(best_i, 1), min(best_i + dur, T - 1)
+        if hi > lo:
+            win[lo:hi] = True
+            mean_logit = (z_bn[lo:hi] * (1.0 / float(hi - lo))).sum()
+    return best, win, mean_logit
+
+
+def self_label(z_own_last, mask_bnt, text_padding_mask):
+    """Self-labelled window per sentence from the last-stage own-clip logits z_own_last [B,T,N] (already
+    scaled by 1/0.07 and padded with -6e4): p = softmax over sentences, q = softmax over time of p/0.07
+    (:103), window length = the sentence's original duration (>= 1; 0 for padded sentences, :113-115).
+    Returns (window [B,N,T] bool, max_logits [B,N])."""
+    B, T, N = z_own_last.shape
+    p = torch.softmax(z_own_last, dim=-1)
+    q = torch.softmax(p / TEMPERATURE, dim=-2)
+    dur = mask_bnt.sum(-1).clamp(min=1)
+    dur = dur.masked_fill(text_padding_mask, 0)
+    win = torch.zeros(B, N, T, dtype=torch.bool)
+    mx = torch.zeros(B, N)
+    for b in range(B):
+        for n in range(N):
+            _, w, ml = best_window(q[b, :, n], z_own_last[b, :, n], int(dur[b, n]))
+            win[b, n] = w
+            mx[b, n] = ml
+    return win, mx
+
+
+def agreement_targets(zd_own_last, zj_own_last, mask_bnt, text_padding_mask, kind: str):
+    """train/loss.py:88-229: new per-clip targets [B,N,T] bool from the agreement of the dual and joint
+    self-labels.  Returns (targets, confidence_ratio)."""
+    B, T, N = zd_own_last.shape
+    jw, jmax = self_label(zj_own_last, mask_bnt, text_padding_mask)
+    dw, dmax = self_label(zd_own_last, mask_bnt, text_padding_mask)
+    inter = (jw & dw).sum(-1).float()
+    union = (jw | dw).sum(-1).float()
+    iou = inter / union.clamp(min=1e-5)
+    valid = ~text_padding_mask
+    conf_text = (dmax >= quantile_linear(dmax[valid], 0.3)) & (jmax >= quantile_linear(jmax[valid], 0.3))
+    conf_iou = iou >= 0.5
+    conf = conf_text & conf_iou
+    if kind == "i":
+        tgt = (jw & dw) & conf[:, :, None]
+    elif kind == "u":
+        tgt = (jw | dw) & conf[:, :, None]
+    elif kind == "keep":
+        tgt = torch.where(conf_iou[:, :, None], jw | dw, mask_bnt)
+    elif kind == "keep-joint":
+        tgt = torch.where(conf_iou[:, :, None], jw, mask_bnt)
+    else:
+        raise ValueError(kind)
+    # exclusion (:217-226): per frame only the first sentence keeps its 1 (sentence 0 always keeps its own
+    # column); sentences left with nothing get their original timestamps back
+    out = torch.zeros_like(tgt)
+    for b in range(B):
+        for t in range(T):
+            hits = torch.nonzero(tgt[b, :, t]).reshape(-1)
+            if hits.numel() > 0 and int(hits[0]) > 0:
+                out[b, int(hits[0]), t] = True
+        out[b, 0, :] = tgt[b, 0, :]
+        for n in range(N):
+            if not out[b, n].any():
+                out[b, n] = mask_bnt[b, n]
+    return out, conf[valid].float().mean()
+
+
+def get_loss_full(logits: dict, start_list, end_list, video_padding_mask, text_padding_mask, args,
+                  abs_text_pos=None):
+    """get_loss (train/loss.py:55-373) with every branch: agreement self-labelling (learn_agreement,
+    temporal_agreement_type), loss_threshold, alignability-head BCE, model in {init, cotrain}.
+    `logits`: the forward dict (+ 'ema-logits_*' for cotrain).  Returns the reference's loss_dict keys.
+
+    Two properties of the reference that this restatement keeps: (1) in `init` mode the -6e4 padding fill
+    of the self-labelling step is applied IN PLACE to the own-clip blocks of the scaled logits the loss is
+    then computed from (torch.diagonal returns a view, :92-100), so padded frames drop out of their own
+    clip's columns; (2) the thresholded text loss indexes the per-text losses with a mask over ALL real
+    sentences (:298), i.e. it assumes every real sentence has a positive."""
+    tpm = _t(text_padding_mask, torch.bool)
+    vpm = _t(video_padding_mask, torch.bool)
+    zd = _t(logits["logits_dual"]) / TEMPERATURE
+    zj = _t(logits["logits_joint"]) / TEMPERATURE
+    B, Sd, T, _, N = zd.shape
+    mask, _, _ = mask_from_time(start_list, end_list, T, N)                # [B,N,T]
+    valid = ~tpm
+    col_valid = valid.reshape(-1)
+    out = {}
+    tgt_bnt = mask
+    if getattr(args, "learn_agreement", 0):
+        if args.model == "cotrain":
+            src_d = _t(logits["ema-logits_dual"]) / TEMPERATURE
+            src_j = _t(logits["ema-logits_joint"]) / TEMPERATURE
+        else:
+            src_d, src_j = zd, zj
+        own_j = own_clip_block(src_j, vpm, tpm)
+        own_d = own_clip_block(src_d, vpm, tpm)
+        if args.model != "cotrain":                                       # property (1)
+            for b in range(B):
+                zj[b, :, :, b, :] = own_j[b]
+                zd[b, :, :, b, :] = own_d[b]
+        tgt_bnt, ratio = agreement_targets(own_d[:, -1], own_j[:, -1], mask, tpm, args.temporal_agreement_type)
+        out["confidence-ratio"] = ratio
+        out["iou-threshold"] = torch.tensor(0.5)
+    tgt = torch.zeros(B, T, B, N, dtype=torch.bool)
+    for b in range(B):
+        tgt[b, :, b, :] = tgt_bnt[b].t()
+    tgt = tgt.reshape(B * T, B * N) & col_valid[None]
+
+    def terms(z):
+        S = z.shape[1]
+        return milnce_terms(z.permute(1, 0, 2, 3, 4).reshape(S, B * T, -1), tgt, col_valid)
+
+    vd, rh, td, ch = terms(zd)
+    vj, _, tj, _ = terms(zj)
+    loss_dual = (vd[:, rh].mean() + td[:, ch].mean()) / 2
+    loss_joint = (vj[:, rh].mean() + tj[:, ch].mean()) / 2
+    out["loss-dual"], out["loss-joint"] = loss_dual, loss_joint
+    thr = float(getattr(args, "loss_threshold", 0.0))
+    head = bool(getattr(args, "use_alignability_head", 0))
+    if thr > 0 or head:
+        md = own_clip_block(zd)[:, -1].max(dim=1).values[valid]           # [M] best frame per real sentence
+        mj = own_clip_block(zj)[:, -1].max(dim=1).values[valid]
+        comb = (md - md.mean()) / md.std() + (mj - mj.mean()) / mj.std()
+        metric = -comb
+        keep = metric <= quantile_linear(metric, thr)                     # [M]
+        keep_c = torch.zeros(B * N, dtype=torch.bool)
+        keep_c[col_valid] = keep
+        rows_th = (tgt & keep_c[None]).any(dim=1)
+        if thr > 0:
+            out["loss-dual-all"], out["loss-joint-all"] = loss_dual, loss_joint
+            cols_th = ch & keep_c
+            loss_dual_th = (vd[:, rows_th].mean() + td[:, cols_th].mean()) / 2
+            loss_joint_th = (vj[:, rows_th].mean() + tj[:, cols_th].mean()) / 2
+            out["loss-dual"], out["loss-joint"] = loss_dual_th, loss_joint_th
+        if head:
+            label = torch.full_like(md, 2.0)
+            qd, qj = quantile_linear(md, 0.5), quantile_linear(mj, 0.5)
+            label[(md > qd) & (mj > qj)] = 1.0
+            label[(md < qd) & (mj < qj)] = 0.0
+            if abs_text_pos is not None:
+                centre = _t(abs_text_pos)[valid].mean(-1)
+                label[(centre < 0.2) | (centre > 0.8)] = 0.0
+            has = ch[col_valid]                                            # real sentences with a positive
+            xj = _t(logits["joint_logits_alignability"])[:, 2, :, 0][valid][has]
+            sel = label != 2.0
+            y = label[sel]
+            pw = 1.0 / y.mean() - 1.0
+            x = xj[sel]
+            sp = lambda v: torch.clamp(v, min=0) + torch.log1p(torch.exp(-v.abs()))     # softplus
+            bce = (pw * y * sp(-x) + (1 - y) * sp(x)).mean()
+            out["loss-joint-bce"] = bce
+            out["alignability_top1"] = ((x > 0) == (y > 0.5)).float().mean()
+    nce_w = 0.0 if getattr(args, "optim_policy", "default") == "bce" else 1.0
+    if thr > 0:
+        out["loss-total"] = (loss_dual + loss_joint) / 2
+        loss = (loss_dual_th + loss_joint_th) / 2
+    else:
+        loss = (loss_dual + loss_joint) / 2
+    if head:
+        loss = loss * nce_w + bce
+    out["loss"] = loss
+    return out

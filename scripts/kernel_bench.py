@@ -101,21 +101,22 @@ def bench_sim(B, S, T, N, d, Bglob, store):
     v = (v / v.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
     t = torch.randn(S, C, d, device=DEV)
     t = (t / t.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
-    start = torch.randint(0, T, (C,), device=DEV).float()
+    start = torch.randint(0, T, (B * N,), device=DEV).float()
     end = start + 4
     valid = torch.ones(C, dtype=torch.uint8, device=DEV)
+    posbits = ops.pos_from_time(start, end, None, B, T, N)
     g = ops.sim_geom(B, S, T, C, N, d, 0)
     rs = torch.empty(2, B * S * T, device=DEV)
     cs = torch.empty(2, S, C, device=DEV)
     ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
     lg = torch.empty(B * S * T, C, dtype=torch.bfloat16, device=DEV) if store else None
-    ms = timeit(lambda: ops.sim_nce_fwd(v, t, C * d, g, start, end, valid, lg, rs, cs, ws))
+    ms = timeit(lambda: ops.sim_nce_fwd(v, t, C * d, g, posbits, valid, lg, rs, cs, ws))
     fl = 2 * B * S * T * C * d
     rec = {"kernel": "sim_nce_fwd", "B": B, "S": S, "T": T, "C": C, "store": store, "ms": round(ms, 4),
            "tflops": round(fl / ms / 1e9, 1)}
     if store:
         rec["logit_write_GBps"] = round(B * S * T * C * 2 / ms / 1e6, 1)
-        ms2 = timeit(lambda: ops.nce_from_logits(lg.view(B, S, T, Bglob, N), g, start, end, valid, rs, cs, ws))
+        ms2 = timeit(lambda: ops.nce_from_logits(lg.view(B, S, T, Bglob, N), g, posbits, valid, rs, cs, ws))
         rec["nce_from_logits_ms"] = round(ms2, 4)
         rec["nce_from_logits_GBps"] = round(B * S * T * C * 2 / ms2 / 1e6, 1)
     print(json.dumps(rec), flush=True)

@@ -18,7 +18,7 @@ TAN_OK = 0
 ERR_NAMES = {-1: "TAN_ERR_SHAPE", -2: "TAN_ERR_ARCH", -3: "TAN_ERR_WORKSPACE", -4: "TAN_ERR_CUDA",
              -5: "TAN_ERR_ARG"}
 ACT_NONE, ACT_QUICKGELU = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class TanError(RuntimeError):
@@ -59,14 +59,16 @@ SIGNATURES = {
     "tan_attention_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "tan_pos_from_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p]),
     "tan_sim_nce_workspace_bytes": (C.c_size_t, [C.POINTER(SimGeom)]),
     "tan_sim_nce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SimGeom), C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                   C.c_void_p]),
     "tan_nce_from_logits": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SimGeom), C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "tan_nce_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
-                                 C.c_void_p]),
+    "tan_nce_reduce": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

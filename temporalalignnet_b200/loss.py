@@ -68,36 +68,49 @@ def _dist():
 
 
 class NceInputs:
-    """Device-side description of the targets: start / end / col_valid over the GLOBAL columns."""
+    """Device-side description of the targets: packed positive bits of the LOCAL clips [B_loc, T, W] and the
+    column-valid mask over the GLOBAL columns; optional row_kill / row_sel / col_sel (see include/tan_b200.h)."""
 
-    def __init__(self, start, end, col_valid, N, b_off, B_glob):
-        self.start, self.end, self.col_valid, self.N, self.b_off, self.B_glob = start, end, col_valid, N, b_off, B_glob
+    def __init__(self, posbits, col_valid, N, T, b_off, B_glob, row_kill=None, row_sel=None, col_sel=None):
+        self.posbits, self.col_valid, self.N, self.T, self.b_off, self.B_glob = posbits, col_valid, N, T, b_off, B_glob
+        self.row_kill, self.row_sel, self.col_sel = row_kill, row_sel, col_sel
 
 
-def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, device, shard: bool) -> NceInputs:
-    """Python lists -> padded [B, N] start/end (train/loss.py:32-39) and the column-valid mask
-    (~text_padding_mask, :235); with `shard`, all-gathered over ranks so that columns are global."""
+def padded_times(start_list, end_list, T: int, N: int, device):
+    """Python lists -> padded [B, N] start/end (train/loss.py:32-39: missing sentences get start = T+100,
+    end = -100, i.e. never positive), via ONE pinned host buffer and one H2D copy."""
     B = len(start_list)
-    start = torch.full((B, N), float(T) + 1e2, dtype=torch.float32)
-    end = torch.full((B, N), -1e2, dtype=torch.float32)
+    host = torch.empty(2, B, N, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    host[0].fill_(float(T) + 1e2)
+    host[1].fill_(-1e2)
     for b in range(B):
         nb = len(start_list[b])
         if nb > N:
             raise TanError(f"clip {b} has {nb} sentences but text_embed has N={N}")
-        start[b, :nb] = torch.as_tensor(start_list[b], dtype=torch.float32)
-        end[b, :nb] = torch.as_tensor(end_list[b], dtype=torch.float32)
-    start = start.to(device, non_blocking=True).view(-1)
-    end = end.to(device, non_blocking=True).view(-1)
-    valid = (~text_padding_mask.to(device).bool()).to(torch.uint8).contiguous().view(-1)
+        if nb:
+            host[0, b, :nb] = torch.as_tensor(start_list[b], dtype=torch.float32)
+            host[1, b, :nb] = torch.as_tensor(end_list[b], dtype=torch.float32)
+    dev = host.to(device, non_blocking=True)
+    return dev[0], dev[1]
+
+
+def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, device, shard: bool,
+                       pos_fn=None) -> NceInputs:
+    """Targets of the `--model init` recipe: bit (b, t, n) = real sentence and start <= t < end
+    (train/loss.py:26-41,:80-85), built on the device by tan_pos_from_time; the column-valid mask
+    (~text_padding_mask, :235) is all-gathered over ranks with `shard` so that columns are global."""
+    B = len(start_list)
+    start, end = padded_times(start_list, end_list, T, N, device)
+    valid = (~text_padding_mask.to(device).bool()).to(torch.uint8).contiguous()
+    pos_fn = ops.pos_from_time if pos_fn is None else pos_fn      # (tests inject a torch checker on CPU)
+    posbits = pos_fn(start.contiguous(), end.contiguous(), valid, B, T, N)
     dist = _dist() if shard else None
     if dist is None:
-        return NceInputs(start, end, valid, N, 0, B)
+        return NceInputs(posbits, valid.view(-1), N, T, 0, B)
     W, rank = dist.get_world_size(), dist.get_rank()
-    packed = torch.stack((start, end, valid.float()))                       # [3, B*N]
-    gathered = torch.empty(W * 3, B * N, dtype=torch.float32, device=device)     # concat along dim 0
-    dist.all_gather_into_tensor(gathered, packed)
-    g = gathered.view(W, 3, B * N).permute(1, 0, 2).reshape(3, W * B * N).contiguous()
-    return NceInputs(g[0].contiguous(), g[1].contiguous(), g[2].to(torch.uint8).contiguous(), N, rank * B, W * B)
+    gathered = torch.empty(W * B * N, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(gathered, valid.view(-1))
+    return NceInputs(posbits, gathered, N, T, rank * B, W * B)
 
 
 def nce_stats_to_loss(out4: torch.Tensor) -> torch.Tensor:
@@ -121,17 +134,19 @@ def gather_text_features(tfeat: torch.Tensor, shared_text: bool, dist) -> torch.
     return g.view(W, S, tfeat.shape[1], d).permute(1, 0, 2, 3).reshape(S, W * tfeat.shape[1], d).contiguous()
 
 
-def finish_loss(row_sums: torch.Tensor, col_sums: torch.Tensor, dist, reduce_fn=None) -> torch.Tensor:
+def finish_loss(row_sums: torch.Tensor, col_sums: torch.Tensor, dist, T: int, reduce_fn=None, row_sel=None,
+                col_sel=None) -> torch.Tensor:
     """Exp-sums -> loss_x.  row_sums [2, R_local], col_sums [2, S, C] (partial over the local rows).
     Distributed: column sums add across ranks (fixed-shift exp sums); row terms are reduced locally and
     their (sum, count) all-reduced, so every rank returns the global-batch loss."""
     reduce_fn = ops.nce_reduce if reduce_fn is None else reduce_fn
     out4 = torch.zeros(4, dtype=torch.float64, device=row_sums.device)
+    S, C = col_sums.shape[1], col_sums.shape[2]
     if dist is None:
-        reduce_fn(row_sums, col_sums, out4)
+        reduce_fn(row_sums, col_sums, out4, S, T, C, row_sel, col_sel)
     else:
         dist.all_reduce(col_sums)
-        reduce_fn(row_sums, col_sums, out4)             # cols now global and identical on every rank
+        reduce_fn(row_sums, col_sums, out4, S, T, C, row_sel, col_sel)   # cols now global, identical on every rank
         rows = out4[:2].clone()
         dist.all_reduce(rows)
         out4 = torch.cat((rows, out4[2:]))
@@ -152,8 +167,8 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
         row_sums = torch.empty(2, B * S * T, dtype=torch.float32, device=dev)
         col_sums = torch.empty(2, S, C, dtype=torch.float32, device=dev)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
-        ops.sim_nce_fwd(vfeat, tfeat, 0 if logits.shared_text else C * d, g, nce.start, nce.end, nce.col_valid, None,
-                        row_sums, col_sums, ws)
+        ops.sim_nce_fwd(vfeat, tfeat, 0 if logits.shared_text else C * d, g, nce.posbits, nce.col_valid, None,
+                        row_sums, col_sums, ws, row_kill=nce.row_kill)
     else:
         if logits.dim() != 5:
             raise TanError(f"logits must be [B,S,T,B,N], got {tuple(logits.shape)}")
@@ -170,8 +185,8 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
         row_sums = torch.empty(2, B * S * T, dtype=torch.float32, device=dev)
         col_sums = torch.empty(2, S, C, dtype=torch.float32, device=dev)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
-        ops.nce_from_logits(x, g, nce.start, nce.end, nce.col_valid, row_sums, col_sums, ws)
-    return finish_loss(row_sums, col_sums, dist)
+        ops.nce_from_logits(x, g, nce.posbits, nce.col_valid, row_sums, col_sums, ws, row_kill=nce.row_kill)
+    return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel)
 
 
 def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding_mask, logits, args,

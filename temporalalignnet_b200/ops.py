@@ -171,20 +171,37 @@ def sim_workspace_bytes(g: SimGeom) -> int:
     return int(lib().tan_sim_nce_workspace_bytes(C.byref(g)))
 
 
-def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride: int, g: SimGeom, start, end, col_valid, logits_out,
-                row_sums, col_sums, workspace) -> None:
+def pos_from_time(start: torch.Tensor, end: torch.Tensor, valid_u8: Optional[torch.Tensor], B: int, T: int, N: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tan_pos_from_time: packed target bits [B, T, ceil(N/32)] (int32 storage of the uint32 words)."""
+    global _launches
+    W = (N + 31) // 32
+    if out is None:
+        out = torch.empty(B, T, W, dtype=torch.int32, device=start.device)
+    if _skip("glue", float(B * T * W)):
+        return out
+    _need(start, torch.float32, "pos_from_time.start")
+    _need(end, torch.float32, "pos_from_time.end")
+    check(lib().tan_pos_from_time(start.data_ptr(), end.data_ptr(), _ptr(valid_u8), B, T, N, out.data_ptr(), _stream()),
+          "tan_pos_from_time")
+    _launches += 1
+    return out
+
+
+def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride: int, g: SimGeom, posbits, col_valid, logits_out,
+                row_sums, col_sums, workspace, row_kill=None) -> None:
     global _launches
     if _skip("sim_nce_fwd", 2.0 * g.B_loc * g.S * g.T * g.C * g.d, 2):
         return
     with _timed("sim_nce_fwd", 2.0 * g.B_loc * g.S * g.T * g.C * g.d):
         check(lib().tan_sim_nce_fwd(vfeat.data_ptr(), tfeat.data_ptr(), tfeat_stage_stride, C.byref(g),
-                                    start.data_ptr(), end.data_ptr(), col_valid.data_ptr(), _ptr(logits_out),
+                                    posbits.data_ptr(), col_valid.data_ptr(), _ptr(row_kill), _ptr(logits_out),
                                     row_sums.data_ptr(), col_sums.data_ptr(), workspace.data_ptr(),
                                     workspace.numel() * workspace.element_size(), _stream()), "tan_sim_nce_fwd")
     _launches += 2
 
 
-def nce_from_logits(logits, g: SimGeom, start, end, col_valid, row_sums, col_sums, workspace) -> None:
+def nce_from_logits(logits, g: SimGeom, posbits, col_valid, row_sums, col_sums, workspace, row_kill=None) -> None:
     global _launches
     is_f32 = int(logits.dtype == torch.float32)
     if not is_f32 and logits.dtype != torch.bfloat16:
@@ -192,19 +209,22 @@ def nce_from_logits(logits, g: SimGeom, start, end, col_valid, row_sums, col_sum
     if _skip("nce_from_logits", float(logits.numel()) * logits.element_size(), 2):
         return
     with _timed("nce_from_logits", float(logits.numel()) * logits.element_size()):
-        check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), start.data_ptr(), end.data_ptr(),
-                                        col_valid.data_ptr(), row_sums.data_ptr(), col_sums.data_ptr(),
-                                        workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-                                        _stream()), "tan_nce_from_logits")
+        check(lib().tan_nce_from_logits(logits.data_ptr(), is_f32, C.byref(g), posbits.data_ptr(),
+                                        col_valid.data_ptr(), _ptr(row_kill), row_sums.data_ptr(),
+                                        col_sums.data_ptr(), workspace.data_ptr(),
+                                        workspace.numel() * workspace.element_size(), _stream()),
+              "tan_nce_from_logits")
     _launches += 2
 
 
-def nce_reduce(row_sums, col_sums, out4_f64, do_rows=True, do_cols=True) -> None:
+def nce_reduce(row_sums, col_sums, out4_f64, S: int, T: int, C_: int, row_sel=None, col_sel=None) -> None:
+    """tan_nce_reduce.  row_sums [2, B_loc*S*T] or None, col_sums [2, S, C] or None; row_sel [B_loc, T] /
+    col_sel [C] uint8 optional selections (thresholded loss)."""
     global _launches
     R = row_sums.numel() // 2 if row_sums is not None else 0
     SC = col_sums.numel() // 2 if col_sums is not None else 0
     if _skip("nce_reduce", float(R + SC)):
         return
-    check(lib().tan_nce_reduce(_ptr(row_sums), R, _ptr(col_sums), SC, int(do_rows), int(do_cols),
+    check(lib().tan_nce_reduce(_ptr(row_sums), R, S, T, _ptr(row_sel), _ptr(col_sums), SC, C_, _ptr(col_sel),
                                out4_f64.data_ptr(), _stream()), "tan_nce_reduce")
     _launches += 1

@@ -76,11 +76,13 @@ def make_state_dict(num_encoder_layers: int, num_decoder_layers: int, width: int
 
 
 def make_batch(B: int, T: int, N: Optional[int] = None, d_in: int = 1024, text_dim: int = 512,
-               seed: int = 888, pad_video_every: int = 0, tag: str = "") -> dict:
+               seed: int = 888, pad_video_every: int = 0, tag: str = "", force_full: bool = False) -> dict:
     """One synthetic batch.  Returns numpy arrays + python lists (the reference's input types).
 
     pad_video_every=k>0 pads a suffix (T/4 frames) of every k-th clip (coverage variant of 8(d)).
     `tag` decorrelates batches drawn with the same seed (e.g. per rank / per step).
+    force_full gives clip 0 all N sentences: the reference's get_mask_from_time only broadcasts when the
+    longest clip has exactly N sentences (train/loss.py:31-40).
     """
     if N is None:
         N = max(T // 8, 1)
@@ -88,6 +90,8 @@ def make_batch(B: int, T: int, N: Optional[int] = None, d_in: int = 1024, text_d
     video = r.standard_normal((B, T, d_in)).astype(np.float32)
     text = r.standard_normal((B, N, text_dim)).astype(np.float32)
     n_b = r.integers(max(N // 2, 1), N + 1, size=B)
+    if force_full:
+        n_b[0] = N
     text_padding_mask = np.zeros((B, N), bool)
     video_padding_mask = np.zeros((B, T), bool)
     start: List[List[float]] = []
@@ -109,3 +113,30 @@ def make_batch(B: int, T: int, N: Optional[int] = None, d_in: int = 1024, text_d
         "video_padding_mask": video_padding_mask, "text_padding_mask": text_padding_mask,
         "start": start, "end": end, "text_str": sentences, "n_b": n_b.astype(np.int64),
     }
+
+
+def make_logit_case(B: int, S: int, T: int, N: int, seed: int = 888, tag: str = "", pad_video_every: int = 0) -> dict:
+    """Synthetic cosine logits [B,S,T,B,N] for loss-only parity cases (no model): uniform noise in
+    [-0.3, 0.3] plus, in every own-clip block, one bump of 2-5 frames per sentence (0.4-0.45; usually at the same place
+    for the dual and the joint model), so that the
+    self-labelling argmax of train/loss.py:136 is decisive (near-ties flip with the summation order).
+    Also EMA logits, alignability-head logits, absolute text positions and a batch whose clip 0 has all N
+    sentences."""
+    batch = make_batch(B, T, N, seed=seed, tag=f"lc{tag}", force_full=True, pad_video_every=pad_video_every)
+    r = _rng(f"logits{tag}", seed)
+    out = {"batch": batch}
+    base = [[(int(r.integers(2, max(T - 6, 3))), int(r.integers(2, 6))) for _ in range(N)] for _ in range(B)]
+    for k in ("logits_dual", "logits_joint", "ema-logits_dual", "ema-logits_joint"):
+        x = (r.random((B, S, T, B, N), dtype=np.float32) * 2 - 1) * 0.3
+        for b in range(B):
+            for n in range(N):
+                c, w = base[b][n]                      # the two models mostly agree (IoU >= 0.5 is exercised)
+                if r.random() < 0.3:
+                    c, w = int(r.integers(2, max(T - 6, 3))), int(r.integers(2, 6))
+                hi = min(c + w, T)
+                x[b, :, c:hi, b, n] += 0.4 + 0.05 * r.random(hi - c, dtype=np.float32)
+        out[k] = x
+    out["dual_logits_alignability"] = r.standard_normal((B, N, 1)).astype(np.float32)
+    out["joint_logits_alignability"] = r.standard_normal((B, S, N, 1)).astype(np.float32)
+    out["abs_text_pos"] = r.random((B, N, 2), dtype=np.float32)
+    return out

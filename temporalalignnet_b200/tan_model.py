@@ -81,12 +81,12 @@ class LazyLogits:
             dev = self.device
             g = ops.sim_geom(B, S, T, C, self.N, d, 0)
             out = torch.empty(B, S, T, C // self.N, self.N, dtype=torch.bfloat16, device=dev)
-            start = torch.zeros(C, dtype=torch.float32, device=dev)
+            posbits = torch.zeros(B, T, (self.N + 31) // 32, dtype=torch.int32, device=dev)
             valid = torch.ones(C, dtype=torch.uint8, device=dev)
             rs = torch.empty(2, B * S * T, dtype=torch.float32, device=dev)
             cs = torch.empty(2, S, C, dtype=torch.float32, device=dev)
             ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
-            ops.sim_nce_fwd(self.vfeat, self.tfeat, 0 if self.shared_text else C * d, g, start, start, valid, out,
+            ops.sim_nce_fwd(self.vfeat, self.tfeat, 0 if self.shared_text else C * d, g, posbits, valid, out,
                             rs, cs, ws)
             self._dense = out
         return self._dense

@@ -47,3 +47,31 @@ def max_abs(a, b):
     a = torch.as_tensor(np.asarray(a), dtype=torch.float64)
     b = torch.as_tensor(np.asarray(b), dtype=torch.float64)
     return float((a - b).abs().max())
+
+
+def pack_posbits(mask_bnt: torch.Tensor) -> torch.Tensor:
+    """[B, N, T] bool -> packed target bits [B, T, ceil(N/32)] int32 (include/tan_b200.h), torch checker."""
+    B, N, T = mask_bnt.shape
+    W = (N + 31) // 32
+    m = torch.zeros(B, T, W * 32, dtype=torch.int64)
+    m[:, :, :N] = mask_bnt.permute(0, 2, 1).to(torch.int64)
+    words = (m.view(B, T, W, 32) << torch.arange(32, dtype=torch.int64)).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+    return words.to(torch.int32)
+
+
+def unpack_posbits(posbits: torch.Tensor, N: int) -> torch.Tensor:
+    """packed [B, T, W] int32 -> [B, N, T] bool."""
+    B, T, W = posbits.shape
+    w = posbits.to(torch.int64) & 0xFFFFFFFF
+    bits = (w[..., None] >> torch.arange(32, dtype=torch.int64)) & 1
+    return bits.view(B, T, W * 32)[:, :, :N].permute(0, 2, 1).bool()
+
+
+def cpu_pos_from_time(start, end, valid, B, T, N):
+    """torch restatement of tan_pos_from_time (checker for CPU tests)."""
+    tt = torch.arange(T, dtype=torch.float32)[None, None, :]
+    m = (start.view(B, N, 1) <= tt) & (tt < end.view(B, N, 1))
+    if valid is not None:
+        m = m & valid.view(B, N, 1).bool()
+    return pack_posbits(m)

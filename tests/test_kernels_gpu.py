@@ -219,8 +219,20 @@ def _sim_inputs(B, S, T, N, d, seed, shared):
     return v, t, start.view(-1).to(DEV), end.view(-1).to(DEV), valid.view(-1).to(DEV)
 
 
-def _sim_ref(v, t, start, end, valid, B, S, T, N, shared, b_off=0, B_loc=None):
-    """fp32 torch reference of the statistics: exp-sums with the fixed shift 1/0.07."""
+def _posbits(ops, start, end, valid, B, T, N, b_off=0, B_loc=None):
+    """Packed target bits of the local clips from tan_pos_from_time, checked against the torch packer."""
+    from tests.helpers import cpu_pos_from_time
+    B_loc = B if B_loc is None else B_loc
+    sl = slice(b_off * N, (b_off + B_loc) * N)
+    bits = ops.pos_from_time(start[sl].contiguous(), end[sl].contiguous(), valid[sl].contiguous(), B_loc, T, N)
+    ref = cpu_pos_from_time(start[sl].cpu(), end[sl].cpu(), valid[sl].cpu(), B_loc, T, N)
+    assert torch.equal(bits.cpu(), ref)
+    return bits
+
+
+def _sim_ref(v, t, start, end, valid, B, S, T, N, shared, b_off=0, B_loc=None, kill=None):
+    """fp32 torch reference of the statistics: exp-sums with the fixed shift 1/0.07.  kill [B_loc, T] bool:
+    own-clip entries of those frames count as exp(-inf)."""
     B_loc = B if B_loc is None else B_loc
     vf = v.float()                                                  # [B_loc,S,T,d]
     tf = t.float() if not shared else t.float()[None].expand(S, -1, -1)     # [S,C,d]
@@ -231,6 +243,8 @@ def _sim_ref(v, t, start, end, valid, B, S, T, N, shared, b_off=0, B_loc=None):
     pos_bt = (start[None, :] <= tt[:, None]) & (tt[:, None] < end[None, :]) & valid.bool()[None, :]    # [T,C]
     own = (torch.arange(C, device=v.device) // N)[None, :] == (b_off + torch.arange(B_loc, device=v.device))[:, None]
     pos = pos_bt[None, :, :] & own[:, None, :]                      # [B_loc,T,C]
+    if kill is not None:
+        e = e * (~(kill[:, :, None] & own[:, None, :]))[:, None].float()
     pe = e * pos[:, None].float()
     row = torch.stack((e.sum(-1).reshape(-1), pe.sum(-1).reshape(-1)))
     col = torch.stack((e.sum(dim=(0, 2)), pe.sum(dim=(0, 2))))     # [2,S,C]
@@ -241,8 +255,8 @@ def _sim_ref(v, t, start, end, valid, B, S, T, N, shared, b_off=0, B_loc=None):
     (4, 1, 32, 4, 512, True), (3, 3, 24, 5, 512, False), (2, 6, 64, 8, 512, False),
     (8, 2, 256, 32, 512, True), (8, 2, 256, 32, 512, False), (2, 2, 200, 70, 768, False), (5, 1, 130, 3, 512, True),
 ])
-@pytest.mark.parametrize("store", [False, True])
-def test_sim_nce_fwd(B, S, T, N, d, shared, store):
+@pytest.mark.parametrize("store,kill", [(False, False), (True, False), (False, True), (True, True)])
+def test_sim_nce_fwd(B, S, T, N, d, shared, store, kill):
     ops = _ops()
     v, t, start, end, valid = _sim_inputs(B, S, T, N, d, 30, shared)
     C = B * N
@@ -251,8 +265,14 @@ def test_sim_nce_fwd(B, S, T, N, d, shared, store):
     cs = torch.empty(2, S, C, device=DEV)
     ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
     logits = torch.full((B, S, T, B, N), float("nan"), dtype=torch.bfloat16, device=DEV) if store else None
-    ops.sim_nce_fwd(v, t, 0 if shared else C * d, g, start, end, valid, logits, rs, cs, ws)
-    cos, row, col = _sim_ref(v, t, start, end, valid, B, S, T, N, shared)
+    posbits = _posbits(ops, start, end, valid, B, T, N)
+    km = None
+    if kill:                                         # padded suffix on every other clip
+        km = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+        km[::2, T - max(T // 4, 1):] = True
+    ops.sim_nce_fwd(v, t, 0 if shared else C * d, g, posbits, valid, logits, rs, cs, ws,
+                    row_kill=km.to(torch.uint8) if kill else None)
+    cos, row, col = _sim_ref(v, t, start, end, valid, B, S, T, N, shared, kill=km)
     # ex2.approx on |z| <= 14.3: relative error ~1e-6 per term; sums of positives
     assert ((rs - row).abs() / row.clamp_min(1e-30)).max().item() < 1e-3
     assert ((cs - col).abs() / col.clamp_min(1e-30)).max().item() < 1e-3
@@ -283,17 +303,61 @@ def test_nce_from_logits(B, S, T, N, dtype):
     rs = torch.empty(2, B * S * T, device=DEV)
     cs = torch.empty(2, S, C, device=DEV)
     ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
-    ops.nce_from_logits(logits.view(B, S, T, B, N), g, start, end, valid, rs, cs, ws)
+    posbits = _posbits(ops, start, end, valid, B, T, N)
+    ops.nce_from_logits(logits.view(B, S, T, B, N), g, posbits, valid, rs, cs, ws)
     assert ((rs - row).abs() / row.clamp_min(1e-30)).max().item() < 1e-4
     assert ((cs - col).abs() / col.clamp_min(1e-30)).max().item() < 1e-4
     out4 = torch.zeros(4, dtype=torch.float64, device=DEV)
-    ops.nce_reduce(rs, cs, out4)
+    ops.nce_reduce(rs, cs, out4, S, T, C)
     rm, cm = row[1] > 0, col[1].reshape(-1) > 0
     ref_v = (row[0][rm].log() - row[1][rm].log()).double().sum()
     ref_t = (col[0].reshape(-1)[cm].log() - col[1].reshape(-1)[cm].log()).double().sum()
     assert abs(out4[1].item() - rm.sum().item()) == 0 and abs(out4[3].item() - cm.sum().item()) == 0
     assert abs(out4[0].item() - ref_v.item()) < 1e-4 * abs(ref_v.item())
     assert abs(out4[2].item() - ref_t.item()) < 1e-4 * abs(ref_t.item())
+    # row / column selections of the thresholded loss (train/loss.py:277-304)
+    gsel = torch.Generator().manual_seed(7)
+    row_sel = (torch.rand(B, T, generator=gsel) < 0.5).to(DEV)
+    col_sel = (torch.rand(C, generator=gsel) < 0.5).to(DEV)
+    out4.zero_()
+    ops.nce_reduce(rs, cs, out4, S, T, C, row_sel.to(torch.uint8), col_sel.to(torch.uint8))
+    rm2 = rm & row_sel[:, None, :].expand(B, S, T).reshape(-1)
+    cm2 = cm & col_sel[None, :].expand(S, C).reshape(-1)
+    ref_v2 = (row[0][rm2].log() - row[1][rm2].log()).double().sum()
+    ref_t2 = (col[0].reshape(-1)[cm2].log() - col[1].reshape(-1)[cm2].log()).double().sum()
+    assert out4[1].item() == rm2.sum().item() and out4[3].item() == cm2.sum().item()
+    assert abs(out4[0].item() - ref_v2.item()) <= 1e-4 * abs(ref_v2.item()) + 1e-9
+    assert abs(out4[2].item() - ref_t2.item()) <= 1e-4 * abs(ref_t2.item()) + 1e-9
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nce_from_logits_killed_rows_and_many_clips(dtype):
+    """Row-kill (the reference's -6e4 fill of padded frames) and the multi-clip-per-CTA walk."""
+    ops = _ops()
+    B, S, T, N, d = 40, 2, 72, 8, 128
+    v, t, start, end, valid = _sim_inputs(B, S, T, N, d, 33, False)
+    C = B * N
+    km = torch.zeros(B, T, dtype=torch.bool, device=DEV)
+    km[1::3, T - 20:] = True
+    cos, _, _ = _sim_ref(v, t, start, end, valid, B, S, T, N, False)
+    logits = cos.to(dtype).contiguous()
+    e = torch.exp((logits.float() - 1.0) / 0.07) * valid.float()
+    tt = torch.arange(T, device=DEV).float()
+    pos_bt = (start[None, :] <= tt[:, None]) & (tt[:, None] < end[None, :]) & valid.bool()[None, :]
+    own = (torch.arange(C, device=DEV) // N)[None, :] == torch.arange(B, device=DEV)[:, None]
+    e = e * (~(km[:, :, None] & own[:, None, :]))[:, None].float()
+    pe = e * (pos_bt[None] & own[:, None, :])[:, None].float()
+    row = torch.stack((e.sum(-1).reshape(-1), pe.sum(-1).reshape(-1)))
+    col = torch.stack((e.sum(dim=(0, 2)), pe.sum(dim=(0, 2))))
+    g = ops.sim_geom(B, S, T, C, N, d, 0)
+    rs = torch.empty(2, B * S * T, device=DEV)
+    cs = torch.empty(2, S, C, device=DEV)
+    ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
+    posbits = _posbits(ops, start, end, valid, B, T, N)
+    ops.nce_from_logits(logits.view(B, S, T, B, N), g, posbits, valid, rs, cs, ws, row_kill=km.to(torch.uint8))
+    assert ((rs - row).abs() / row.clamp_min(1e-30)).max().item() < 1e-4
+    assert ((cs - col).abs() / col.clamp_min(1e-30)).max().item() < 1e-4
+    assert ((rs[1] > 0) == (row[1] > 0)).all() and ((cs[1] > 0) == (col[1] > 0)).all()
 
 
 def test_sim_sharded_rows_add_up():
@@ -308,7 +372,8 @@ def test_sim_sharded_rows_add_up():
         rs = torch.empty(2, B_loc * S * T, device=DEV)
         cs = torch.empty(2, S, C, device=DEV)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
-        ops.sim_nce_fwd(vv.contiguous(), t, C * d, g, start, end, valid, None, rs, cs, ws)
+        posbits = _posbits(ops, start, end, valid, B, T, N, b_off, B_loc)
+        ops.sim_nce_fwd(vv.contiguous(), t, C * d, g, posbits, valid, None, rs, cs, ws)
         return rs, cs
 
     rs_full, cs_full = run(v, 0, B)

@@ -13,6 +13,7 @@ import torch.multiprocessing as mp
 
 from oracle import tan_oracle as O
 from temporalalignnet_b200 import synth
+from tests.helpers import cpu_pos_from_time, unpack_posbits
 
 
 def _free_port():
@@ -23,7 +24,7 @@ def _free_port():
     return p
 
 
-def _cpu_reduce(row_sums, col_sums, out4, do_rows=True, do_cols=True):
+def _cpu_reduce(row_sums, col_sums, out4, S=None, T=None, C=None, row_sel=None, col_sel=None):
     """torch restatement of tan_nce_reduce (checker for the CPU test)."""
     R = row_sums.shape[1]
     m = row_sums[1] > 0
@@ -41,10 +42,11 @@ def _exp_sums(vn, tn, nce, B_loc, S, T, N):
     valid = nce.col_valid.bool()
     e = torch.exp((cos - 1.0) / 0.07) * valid.float()
     C = tn.shape[1]
-    tt = torch.arange(T).float()
-    pos_t = (nce.start[None] <= tt[:, None]) & (tt[:, None] < nce.end[None]) & valid[None]
-    own = (torch.arange(C) // N)[None] == (nce.b_off + torch.arange(B_loc))[:, None]
-    pe = e * (pos_t[None] & own[:, None, :])[:, None].float()
+    pos_own = unpack_posbits(nce.posbits, N).permute(0, 2, 1)                # [B_loc, T, N] targets of the local clips
+    pos = torch.zeros(B_loc, T, C, dtype=torch.bool)
+    for b in range(B_loc):
+        pos[b, :, (nce.b_off + b) * N:(nce.b_off + b + 1) * N] = pos_own[b]
+    pe = e * (pos & valid[None, None])[:, None].float()
     row = torch.stack((e.sum(-1).reshape(-1), pe.sum(-1).reshape(-1)))
     col = torch.stack((e.sum(dim=(0, 2)), pe.sum(dim=(0, 2))))
     return row.float(), col.float()
@@ -75,14 +77,16 @@ def _worker(rank, world, port, ret):
     jv, jt = orc.get_joint_feature(video, vpm, t, tpm)
     jvn = jv / jv.norm(dim=-1, keepdim=True)
     jtn = (jt / jt.norm(dim=-1, keepdim=True)).permute(1, 0, 2, 3).reshape(D, B_loc * N, -1)
-    nce = L.prepare_nce_inputs(full["start"][sl], full["end"][sl], tpm, T, N, torch.device("cpu"), shard=True)
-    assert nce.b_off == rank * B_loc and nce.B_glob == Bg and nce.start.numel() == Bg * N
+    nce = L.prepare_nce_inputs(full["start"][sl], full["end"][sl], tpm, T, N, torch.device("cpu"), shard=True,
+                               pos_fn=cpu_pos_from_time)
+    assert nce.b_off == rank * B_loc and nce.B_glob == Bg and nce.col_valid.numel() == Bg * N
+    assert tuple(nce.posbits.shape) == (B_loc, T, 1)
     losses = []
     for vfeat, tfeat, shared, S in ((vn, tn, True, E), (jvn, jtn, False, D)):
         tg = L.gather_text_features(tfeat.contiguous(), shared, dist)
         tg3 = tg[None].expand(S, -1, -1) if shared else tg
         row, col = _exp_sums(vfeat, tg3, nce, B_loc, S, T, N)
-        losses.append(L.finish_loss(row, col.contiguous(), dist, reduce_fn=_cpu_reduce))
+        losses.append(L.finish_loss(row, col.contiguous(), dist, T, reduce_fn=_cpu_reduce))
     loss = float((losses[0] + losses[1]) / 2)
     if rank == 0:
         ref_out = orc.forward(torch.from_numpy(full["video"]), torch.from_numpy(full["text"]),
@@ -110,9 +114,11 @@ def test_prepare_nce_inputs_single_process_layout():
     from temporalalignnet_b200 import loss as L
     b = synth.make_batch(3, 20, 5, seed=2)
     nce = L.prepare_nce_inputs(b["start"], b["end"], torch.from_numpy(b["text_padding_mask"]), 20, 5,
-                               torch.device("cpu"), shard=False)
+                               torch.device("cpu"), shard=False, pos_fn=cpu_pos_from_time)
     mask, start, end = O.mask_from_time(b["start"], b["end"], 20, 5)
-    assert torch.equal(nce.start.view(3, 5), start) and torch.equal(nce.end.view(3, 5), end)
+    assert torch.equal(unpack_posbits(nce.posbits, 5), mask & ~torch.from_numpy(b["text_padding_mask"])[:, :, None])
+    s2, e2 = L.padded_times(b["start"], b["end"], 20, 5, torch.device("cpu"))
+    assert torch.equal(s2, start) and torch.equal(e2, end)
     assert torch.equal(nce.col_valid.view(3, 5).bool(), ~torch.from_numpy(b["text_padding_mask"]))
     m2, s2, e2 = L.get_mask_from_time(b["start"], b["end"], 20, 5, device="cpu")
     assert torch.equal(m2[:, :mask.shape[1]], mask[:, :m2.shape[1]])
