@@ -214,6 +214,38 @@ TAN_API int tan_nce_reduce(const float* row_sums, int64_t R, int S, int T, const
                    const float* col_sums, int64_t SC, int C, const uint8_t* col_sel, double* out,
                    void* stream);
 
+/* ---- own-clip similarity blocks, agreement self-labelling ----------------------------------------- */
+
+/* out[b, j, t, n] = <vfeat[b, s_first + j, t], tfeat_(s)[b * N + n]>  for j < s_count: the own-clip (diagonal)
+ * blocks of the [B,S,T,B,N] cosine matrix, fp32 [B, s_count, T, N].  vfeat [B*S*T, d] bf16; tfeat [B*N, d]
+ * (tfeat_stage_stride == 0) or [S, B*N, d] (stride B*N*d) bf16; B counts the LOCAL clips and tfeat holds their
+ * sentences.  d % 64 == 0.  Replaces torch.diagonal(logits, dim1=0, dim2=3) at train/loss.py:92-95,:150-153,
+ * :280-283 (last stage) and the eval einsum 'bstc,b(s)kc->bstk' at model/tan_model.py:261-262,:280-281. */
+TAN_API int tan_own_clip_sim(const void* vfeat, const void* tfeat, int64_t tfeat_stage_stride, int B, int S, int T,
+                     int N, int d, int s_first, int s_count, float* out, void* stream);
+
+/* Self-labelling scan of one model (train/loss.py:96-145): own [B, T, N] fp32 own-clip cosines of the last
+ * stage; with z = own / 0.07 and -6e4 on padded frames / sentences: p = softmax over sentences, q = softmax
+ * over time of p / 0.07; for every sentence the window of its original duration (popcount of its posbits
+ * column, >= 1; padded sentences: none) with the best mean q, never frames 0 and T-1, first best wins.
+ *   win [B, N, 2] int32 kept frame range [lo, hi) (lo == hi: none); mean_logit [B, N] = mean of z over it;
+ *   max_logit [B, N] = max_t z (train/loss.py:280; padded frames filled only if fill_max != 0, which is the
+ *   reference's in-place side effect in `init` mode).
+ * video_padding_mask [B, T] uint8 or NULL, text_padding_mask [B, N] uint8 (1 = padded).
+ * Replaces the [B,N,T,T] circulant box filter (2.1 GB at BASELINE config 5). */
+TAN_API size_t tan_agree_scan_workspace_bytes(int B, int T, int N);
+TAN_API int tan_agree_scan(const float* own, const uint32_t* posbits, const uint8_t* video_padding_mask,
+                   const uint8_t* text_padding_mask, int B, int T, int N, int fill_max, int* win,
+                   float* mean_logit, float* max_logit, void* workspace, size_t workspace_bytes, void* stream);
+
+/* New target bits from the two models' windows (train/loss.py:196-226).  kind: 0 'i' (intersection where
+ * replace[b,n]), 1 'u' (union where replace), 2 'keep' (union where replace, else the old timestamps),
+ * 3 'keep-joint' (joint window where replace, else old); then at most one sentence per frame (the first)
+ * and sentences left with no frame get their old timestamps back.  replace [B, N] uint8. */
+TAN_API int tan_agree_targets(const uint32_t* old_posbits, const int* win_joint, const int* win_dual,
+                      const uint8_t* replace, int B, int T, int N, int kind, uint32_t* new_posbits,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,13 +25,19 @@ def main():
     Bg = B_loc * world
     sd = synth.make_state_dict(E, D)
     batch = synth.make_batch(Bg, T, N, pad_video_every=3)
-    m = TemporalAligner(E, D, random_pos_start=0)
+    sd = synth.make_state_dict(E, D, use_alignability_head=True)
+    m = TemporalAligner(E, D, random_pos_start=0, use_alignability_head=1)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     m = m.to(dev)
-    args = types.SimpleNamespace(model="init", sim="cos", learn_agreement=0, loss_threshold=0.0,
-                                 use_alignability_head=0, optim_policy="default")
+    arg_sets = [
+        dict(model="init", sim="cos", learn_agreement=0, loss_threshold=0.0, use_alignability_head=0,
+             optim_policy="default", temporal_agreement_type="keep"),
+        # every loss branch: the quantiles / standardisation / BCE span the global batch
+        dict(model="init", sim="cos", learn_agreement=1, loss_threshold=0.5, use_alignability_head=1,
+             optim_policy="default", temporal_agreement_type="keep"),
+    ]
 
-    def run(lo, hi, shard):
+    def run(lo, hi, shard, args):
         video = torch.from_numpy(batch["video"][lo:hi]).to(dev)
         text = torch.from_numpy(batch["text"][lo:hi]).to(dev)
         vpm = torch.from_numpy(batch["video_padding_mask"][lo:hi]).to(dev)
@@ -41,14 +47,18 @@ def main():
                       video, text, vpm.float(), tpm.float(), out, args, None, shard_batch=shard)
         return {k: float(v) for k, v in ld.items()}
 
-    sharded = run(rank * B_loc, (rank + 1) * B_loc, True)
-    single = run(0, Bg, False)                      # every rank recomputes the global batch alone
-    err = max(abs(sharded[k] - single[k]) / abs(single[k]) for k in single)
-    t = torch.tensor([err], device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        print(f"world={world} sharded={sharded} single={single} max rel err over ranks {float(t):.2e}")
-    assert float(t) < 1e-5, "sharded loss differs from the single-GPU loss of the same global batch"
+    for kw in arg_sets:
+        args = types.SimpleNamespace(**kw)
+        sharded = run(rank * B_loc, (rank + 1) * B_loc, True, args)
+        single = run(0, Bg, False, args)            # every rank recomputes the global batch alone
+        assert set(sharded) == set(single)
+        err = max(abs(sharded[k] - single[k]) / max(abs(single[k]), 1e-6) for k in single)
+        t = torch.tensor([err], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"world={world} learn={kw['learn_agreement']} sharded={sharded} single={single} "
+                  f"max rel err over ranks {float(t):.2e}")
+        assert float(t) < 1e-5, "sharded loss differs from the single-GPU loss of the same global batch"
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,22 +1,28 @@
 // tan_attention_bf16: multi-head softmax attention core on tcgen05 tensor cores, head_dim 64,
 // arbitrary key-padding mask, Lq != Lk allowed (cross-attention).
 //
-// One CTA per (128-query tile, head, clip), 192 threads, two CTAs per SM:
-//   warp 0      TMA producer (Q tile once, K/V blocks of 64 keys through a 3-stage ring) + TMEM allocator
-//   warp 1      MMA issuer:  S  = Q K_j^T     (M=128, N=64, K=64; both operands K-major, 128B swizzle)
-//                            O_j = P_j V_j     (M=128, N=64, K=64; V is consumed as it lies in HBM,
+// One CTA per (clip, head), 192 threads, two CTAs per SM.  The CTA walks ALL 128-query tiles of its (clip, head)
+// and, inside each, the 64-key blocks; every pipeline (Q tiles, K ring, V ring, S / P / O buffers) keeps running
+// across query-tile boundaries, so the launch / TMEM-allocation / first-load latency is paid once per (clip,
+// head) instead of once per 4-5 key blocks (the per-tile CTAs of the first versions spent about half of their
+// ~8 us lifetime in that prologue: profiles/r01b_prof_attn, 15 % tensor-pipe activity).
+//   warp 0      TMA producer: Q tile (double buffered), K blocks (2-stage ring, freed by QK), V blocks (3-stage
+//               ring, freed by PV) + TMEM allocator
+//   warp 1      MMA issuer:  S_g = Q K_g^T    (M=128, N=64, K=64; both operands K-major, 128B swizzle)
+//                            O  += P_g V_g     (M=128, N=64, K=64; V is consumed as it lies in HBM,
 //                                               [keys, 64] = MN-major B operand, no transpose anywhere)
 //   warps 2-5   softmax: thread = one query row (TMEM lane), so row max / row sum are thread-local
-//               (no shuffles); S comes from TMEM with tcgen05.ld, P_j = exp2(S - m) goes back to shared
+//               (no shuffles); S_g comes from TMEM with tcgen05.ld, P_g = exp2(S_g - m) goes back to shared
 //               memory as the bf16 A operand of the second MMA (128B-swizzled K-major, the layout TMA
-//               would have produced), O accumulates in registers: O = O * alpha_j + O_j (online softmax),
-//               so nothing in TMEM ever needs rescaling and the only hand-offs are three mbarriers per block.
-//               S, P and O_j are double buffered and the O_j accumulation is deferred by one block, so QK_{j+1}
-//               and PV_j execute under the softmax of the neighbouring blocks.
-// The L x L score matrix never exists outside TMEM.  Per 64-key block a CTA reads 64 KB out of TMEM
-// (S and O_j, ~64 B/clk/SM) and issues 8192 exp2 (16/clk/SM): both ~1k cycles against 256 cycles of MMA, so
-// the kernel is bound by TMEM-read / MUFU throughput, not by the tensor pipe; two resident CTAs overlap one
-// CTA's softmax with the other's loads and MMAs.
+//               would have produced).
+// O ACCUMULATES IN TMEM across the key blocks (double buffered across query tiles) and is read once per tile.
+// The reference max m of a row is only raised when a block's maximum exceeds it by more than 8 (log2 domain,
+// i.e. P <= 256: harmless for bf16 P and fp32 sums); only then the warp rescales its 32 rows of O in TMEM
+// (tcgen05.ld / st) -- after the first block this almost never happens.  A TMEM read moves 64 B/clk/SM, so
+// reading S_g (32 KB per block) costs as much as the block's 8192 exp2 on the MUFU pipe (512 clk each), both 2x
+// the two MMAs: that, not the tensor pipe, is the floor of head_dim-64 attention.  S and P are double buffered
+// so QK_{g+1} and PV_g execute under the softmax of the neighbouring blocks.  The L x L score matrix never
+// exists outside TMEM.
 #include "common.cuh"
 
 namespace tanb {
@@ -26,8 +32,9 @@ constexpr int kAttBK = 64;
 constexpr int kAttThreads = 192;
 constexpr int kAttQBytes = kAttBQ * 128;      // 16 KB
 constexpr int kAttKVBytes = kAttBK * 128;     // 8 KB
-constexpr int kAttStages = 3;
-constexpr int kAttSmem = kAttQBytes /*Q*/ + kAttStages * 2 * kAttKVBytes /*K,V ring*/ + 2 * kAttQBytes /*P x 2*/ +
+constexpr int kAttKStages = 2;
+constexpr int kAttVStages = 3;
+constexpr int kAttSmem = 2 * kAttQBytes /*Q x 2*/ + (kAttKStages + kAttVStages) * kAttKVBytes + 2 * kAttQBytes /*P x 2*/ +
                          1024 /*bars*/ + 1024 /*alignment slack*/;
 
 __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
@@ -38,36 +45,43 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  int64_t ldo, int Lq, int Lk) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAttQBytes;                 // [3][8 KB]
-  uint8_t* sV = sK + kAttStages * kAttKVBytes;   // [3][8 KB]
-  uint8_t* sP = sV + kAttStages * kAttKVBytes;   // [2][16 KB]
+  uint8_t* sQ = smem;                               // [2][16 KB]
+  uint8_t* sK = sQ + 2 * kAttQBytes;                // [2][8 KB]
+  uint8_t* sV = sK + kAttKStages * kAttKVBytes;     // [3][8 KB]
+  uint8_t* sP = sV + kAttVStages * kAttKVBytes;     // [2][16 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttQBytes);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* kv_full = bars + 1;       // [3]
-  uint64_t* kv_empty = bars + 4;      // [3]
-  uint64_t* s_full = bars + 7;        // [2]
-  uint64_t* p_ready = bars + 9;       // [2] count 4 (one arrive per softmax warp)
-  uint64_t* o_full = bars + 11;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2] the tile's last QK has completed
+  uint64_t* k_full = bars + 4;        // [2]
+  uint64_t* k_empty = bars + 6;       // [2]
+  uint64_t* v_full = bars + 8;        // [3]
+  uint64_t* v_empty = bars + 11;      // [3]
+  uint64_t* s_full = bars + 14;       // [2]
+  uint64_t* p_ready = bars + 16;      // [2] count 4 (one arrive per softmax warp)
+  uint64_t* pv_done = bars + 18;      // [2] PV_g has completed (g & 1): P buffer free, O stable
+  uint64_t* o_free = bars + 20;       // [2] count 4: the tile's O has been read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = qt * kAttBQ;
+  const int nq = (Lq + kAttBQ - 1) / kAttBQ;
   const int nb = (Lk + kAttBK - 1) / kAttBK;
+  const int G = nq * nb;                            // (query tile, key block) pairs, g = qt * nb + j
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      mbar_init(q_full, 1);
-      for (int i = 0; i < kAttStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&o_full[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+        mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
+      }
+      for (int i = 0; i < kAttVStages; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);        // S[2]: columns [0,64), [64,128); O_j[2]: [128,192), [192,256)
+    tmem_alloc(tmem_slot, 256);        // S[2]: columns [0,64), [64,128); O[2]: [128,192), [192,256)
     tmem_relinquish();
   }
   tc_fence_before();
@@ -80,14 +94,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAttQBytes);
-      tma_load_2d(sQ, &tmQ, q_full, h * 64, b * Lq + q0);
-      for (int j = 0; j < nb; ++j) {
-        const int st = j % kAttStages;
-        mbar_wait(&kv_empty[st], ((j / kAttStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kAttKVBytes);
-        tma_load_2d(sK + st * kAttKVBytes, &tmK, &kv_full[st], h * 64, b * Lk + j * kAttBK);
-        tma_load_2d(sV + st * kAttKVBytes, &tmV, &kv_full[st], h * 64, b * Lk + j * kAttBK);
+      for (int qt = 0; qt < nq; ++qt) {
+        const int qb = qt & 1;
+        if (qt >= 2) mbar_wait(&q_empty[qb], ((qt >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&q_full[qb], kAttQBytes);
+        tma_load_2d(sQ + qb * kAttQBytes, &tmQ, &q_full[qb], h * 64, b * Lq + qt * kAttBQ);
+        for (int j = 0; j < nb; ++j) {
+          const int g = qt * nb + j;
+          const int ks = g % kAttKStages, vs = g % kAttVStages;
+          mbar_wait(&k_empty[ks], ((g / kAttKStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[ks], kAttKVBytes);
+          tma_load_2d(sK + ks * kAttKVBytes, &tmK, &k_full[ks], h * 64, b * Lk + j * kAttBK);
+          mbar_wait(&v_empty[vs], ((g / kAttVStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[vs], kAttKVBytes);
+          tma_load_2d(sV + vs * kAttKVBytes, &tmV, &v_full[vs], h * 64, b * Lk + j * kAttBK);
+        }
       }
     }
     __syncwarp();
@@ -95,40 +116,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ===== MMA issuer =====
     constexpr uint32_t idesc_qk = umma_idesc_bf16(kAttBQ, kAttBK);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(kAttBQ, 64) | (1u << 16);     // B (= V) is MN-major
-    // S and O_j are double buffered: QK_{j+2} is issued as soon as S_j has been consumed, PV_j as soon as
-    // P_j is staged, so the softmax warps (the bottleneck) always find their next S tile ready.
-    auto issue_qk = [&](int j) {
-      const int st = j % kAttStages;
-      mbar_wait(&kv_full[st], (j / kAttStages) & 1);
+    // S is double buffered: QK_{g+2} is issued as soon as S_g has been consumed, PV_g as soon as P_g is staged,
+    // so the softmax warps (the bottleneck) always find their next S tile ready -- also across query tiles.
+    auto issue_qk = [&](int g) {
+      const int qt = g / nb, j = g - qt * nb;
+      const int qb = qt & 1, ks = g % kAttKStages;
+      if (j == 0) mbar_wait(&q_full[qb], (qt >> 1) & 1);
+      mbar_wait(&k_full[ks], (g / kAttKStages) & 1);
       tc_fence_after();
       if (lane == 0) {
-        const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ));
-        const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + st * kAttKVBytes));
+        const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + qb * kAttQBytes));
+        const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * kAttKVBytes));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + (j & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        tc_commit(&s_full[j & 1]);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + (g & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        tc_commit(&s_full[g & 1]);
+        tc_commit(&k_empty[ks]);
+        if (j == nb - 1) tc_commit(&q_empty[qb]);
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
     issue_qk(0);
-    if (nb > 1) issue_qk(1);
-    for (int j = 0; j < nb; ++j) {
-      mbar_wait(&p_ready[j & 1], (j >> 1) & 1);  // P_j is in shared memory, S_j and O_{j-2} have been consumed
+    if (G > 1) issue_qk(1);
+    for (int g = 0; g < G; ++g) {
+      const int qt = g / nb, j = g - qt * nb;
+      const int ob = qt & 1, vs = g % kAttVStages;
+      mbar_wait(&p_ready[g & 1], (g >> 1) & 1);  // P_g is in shared memory, S_g consumed, O rescaled if needed
+      if (j == 0 && qt >= 2) mbar_wait(&o_free[ob], ((qt >> 1) - 1) & 1);   // tile qt-2 has left this O buffer
+      mbar_wait(&v_full[vs], (g / kAttVStages) & 1);
       tc_fence_after();
       if (lane == 0) {
-        const int st = j % kAttStages;
-        const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + (j & 1) * kAttQBytes));
-        const uint64_t dv = umma_desc_k_sw128(smem_u32(sV + st * kAttKVBytes));
+        const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + (g & 1) * kAttQBytes));
+        const uint64_t dv = umma_desc_k_sw128(smem_u32(sV + vs * kAttKVBytes));
         // 16 keys per MMA: +32 B along P's rows (K-major), +16 rows x 128 B = 2048 B in V (MN-major)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(tmem_base + 128 + (j & 1) * 64, dp + 2 * k, dv + 128 * k, idesc_pv, k != 0);
-        tc_commit(&o_full[j & 1]);
-        tc_commit(&kv_empty[st]);                // K_j (read by the earlier QK MMAs) and V_j are free
+          umma_bf16_ss(tmem_base + 128 + ob * 64, dp + 2 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
+        tc_commit(&pv_done[g & 1]);
+        tc_commit(&v_empty[vs]);
       }
       __syncwarp();
-      if (j + 2 < nb) issue_qk(j + 2);
+      if (g + 2 < G) issue_qk(g + 2);
     }
   } else {
     // ===== softmax / output (warps 2..5) =====
@@ -137,105 +164,135 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;    // 1/sqrt(64) folded with log2(e)
     const uint8_t* mb = kpm != nullptr ? kpm + static_cast<int64_t>(b) * Lk : nullptr;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
 
-    // o <- o * alpha_j + O_j, deferred by one block so that PV_j runs under the softmax of block j+1
-    auto accumulate = [&](int j, float alpha) {
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+    for (int qt = 0; qt < nq; ++qt) {
+      const int q0 = qt * kAttBQ;
+      const uint32_t t_o = t_lane + 128 + (qt & 1) * 64;
+      const bool live = q0 + quarter * 32 < Lq;        // warp-uniform: this warp owns at least one real query row
+      float m_ref = -INFINITY, l_run = 0.f;
+
+      for (int j = 0; j < nb; ++j) {
+        const int g = qt * nb + j;
+        mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
+        if (live) {
+          // key mask of this block as two warp-uniform words (bit set = ignore key)
+          const int k0 = j * kAttBK + lane, k1 = k0 + 32;
+          const bool ig0 = k0 >= Lk || (mb != nullptr && mb[k0] != 0);
+          const bool ig1 = k1 >= Lk || (mb != nullptr && mb[k1] != 0);
+          const uint32_t w0 = __ballot_sync(0xffffffffu, ig0), w1 = __ballot_sync(0xffffffffu, ig1);
+          uint32_t r0[32], r1[32];
+          const uint32_t t_s = t_lane + (g & 1) * 64;
+          tmem_ld_32x32(t_s, r0);
+          tmem_ld_32x32(t_s + 32, r1);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+          if ((w0 | w1) != 0u) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if ((w0 >> c) & 1u) r0[c] = 0xff800000u;  // -inf
+              if ((w1 >> c) & 1u) r1[c] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[c]), __uint_as_float(r1[c])));
+          mx *= sl2;                                  // sl2 > 0: -inf stays -inf
+          // lazy reference max: raise it only when this block exceeds it by more than 2^8
+          const bool need = (j == 0) ? (mx > m_ref) : (mx > m_ref + 8.0f);
+          if (j > 0 && __any_sync(0xffffffffu, need)) {
+            // rescale this warp's rows of O (and l) to the new reference; PV_{g-1} must have completed
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            tc_fence_after();
+            const float m_new = need ? mx : m_ref;
+            const float alpha = need ? fast_exp2(m_ref - m_new) : 1.f;    // m_ref = -inf -> 0 (O and l are 0 then)
+            uint32_t a0[32];
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              tmem_ld_32x32(t_o + hlf * 32, a0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) a0[c] = __float_as_uint(__uint_as_float(a0[c]) * alpha);
+              tmem_st_32x32(t_o + hlf * 32, a0);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_ref = m_new;
+          } else if (need) {
+            m_ref = mx;                               // first block of the tile
+          }
+          const float nm = (m_ref == -INFINITY) ? 0.f : -m_ref;
+          float ls = 0.f;
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r0[2 * c]), sl2, nm));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r0[2 * c + 1]), sl2, nm));
+            const float p2 = fast_exp2(fmaf(__uint_as_float(r1[2 * c]), sl2, nm));
+            const float p3 = fast_exp2(fmaf(__uint_as_float(r1[2 * c + 1]), sl2, nm));
+            ls += (p0 + p1) + (p2 + p3);
+            pk[c] = pack_bf16x2(p0, p1);            // keys 2c, 2c+1
+            pk[16 + c] = pack_bf16x2(p2, p3);       // keys 32+2c, 32+2c+1
+          }
+          l_run += ls;
+          // sP[g&1] was the A operand of PV_{g-2}
+          if (g >= 2) mbar_wait(&pv_done[g & 1], ((g >> 1) - 1) & 1);
+          // P row: 64 keys = 128 bytes = 8 chunks of 8 keys
+          uint8_t* sPg = sP + (g & 1) * kAttQBytes;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(sPg + att_swz(row, ch)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          fence_proxy_async_smem();                  // P visible to the tensor core (async proxy)
+        }
+        tc_fence_before();                           // S reads / O writes retired before the MMAs that follow p_ready
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g & 1]);
+      }
+      // all MMAs of the tile have completed when its last PV has
+      const int gl = qt * nb + nb - 1;
+      mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1);
       tc_fence_after();
-      uint32_t a0[32], a1[32];
-      const uint32_t t_o = t_lane + 128 + (j & 1) * 64;
-      tmem_ld_32x32(t_o, a0);
-      tmem_ld_32x32(t_o + 32, a1);
-      tmem_ld_wait();
+      if (live) {
+        float o[64];
+        {
+          uint32_t a0[32], a1[32];
+          tmem_ld_32x32(t_o, a0);
+          tmem_ld_32x32(t_o + 32, a1);
+          tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        o[c] = fmaf(o[c], alpha, __uint_as_float(a0[c]));
-        o[32 + c] = fmaf(o[32 + c], alpha, __uint_as_float(a1[c]));
+          for (int c = 0; c < 32; ++c) { o[c] = __uint_as_float(a0[c]); o[32 + c] = __uint_as_float(a1[c]); }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[qt & 1]);   // the next-but-one tile may overwrite this O buffer
+        // normalise, stage this warp's 32 rows in ITS slice of the P buffer the next block will use (its last
+        // reader, PV_{gl-1}, has completed and only this warp writes these rows), then write whole 128-byte
+        // rows: lane = (row % 4, 16-byte chunk)
+        uint8_t* stg = sP + ((gl + 1) & 1) * kAttQBytes;
+        const float inv = 1.f / l_run;               // l == 0 (all keys masked) -> NaN, as torch
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          uint4 u;
+          u.x = pack_bf16x2(o[8 * ch] * inv, o[8 * ch + 1] * inv);
+          u.y = pack_bf16x2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv);
+          u.z = pack_bf16x2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv);
+          u.w = pack_bf16x2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv);
+          *reinterpret_cast<uint4*>(stg + att_swz(row, ch)) = u;
+        }
+        __syncwarp();
+        const int rr = lane >> 3, cc = lane & 7;
+        bf16* ob = out + (static_cast<int64_t>(b) * Lq + q0 + quarter * 32) * ldo + h * 64 + cc * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + rr;
+          if (q0 + quarter * 32 + rl < Lq)
+            *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(rl) * ldo) =
+                *reinterpret_cast<const uint4*>(stg + att_swz(quarter * 32 + rl, cc));
+        }
+        __syncwarp();                                // the staged rows are read before the next block's P overwrites them
+      } else {
+        if (lane == 0) mbar_arrive(&o_free[qt & 1]);
       }
-      tc_fence_before();                         // O_j reads retired before PV_{j+2} (ordered by p_ready)
-    };
-
-    for (int j = 0; j < nb; ++j) {
-      // key mask of this block as two warp-uniform words (bit set = ignore key)
-      const int k0 = j * kAttBK + lane, k1 = k0 + 32;
-      const bool ig0 = k0 >= Lk || (mb != nullptr && mb[k0] != 0);
-      const bool ig1 = k1 >= Lk || (mb != nullptr && mb[k1] != 0);
-      const uint32_t w0 = __ballot_sync(0xffffffffu, ig0), w1 = __ballot_sync(0xffffffffu, ig1);
-
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t t_s = t_lane + (j & 1) * 64;
-      tmem_ld_32x32(t_s, r0);
-      tmem_ld_32x32(t_s + 32, r1);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float a = ((w0 >> c) & 1u) ? -INFINITY : __uint_as_float(r0[c]) * sl2;
-        const float bq = ((w1 >> c) & 1u) ? -INFINITY : __uint_as_float(r1[c]) * sl2;
-        r0[c] = __float_as_uint(a);
-        r1[c] = __float_as_uint(bq);
-        mx = fmaxf(mx, fmaxf(a, bq));
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2(m_run - m_new);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      m_run = m_new;
-      float ls = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float p0 = fast_exp2(__uint_as_float(r0[2 * c]) - m_use);
-        const float p1 = fast_exp2(__uint_as_float(r0[2 * c + 1]) - m_use);
-        const float p2 = fast_exp2(__uint_as_float(r1[2 * c]) - m_use);
-        const float p3 = fast_exp2(__uint_as_float(r1[2 * c + 1]) - m_use);
-        ls += (p0 + p1) + (p2 + p3);
-        pk[c] = pack_bf16x2(p0, p1);            // keys 2c, 2c+1
-        pk[16 + c] = pack_bf16x2(p2, p3);       // keys 32+2c, 32+2c+1
-      }
-      l_run = l_run * alpha + ls;
-      // P row: 64 keys = 128 bytes = 8 chunks of 8 keys (sP[j&1] is free: o_full_{j-2} was awaited last iteration)
-      uint8_t* sPj = sP + (j & 1) * kAttQBytes;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        *reinterpret_cast<uint4*>(sPj + att_swz(row, ch)) =
-            make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-      fence_proxy_async_smem();                  // P visible to the tensor core (async proxy)
-      tc_fence_before();                         // S reads retired before QK_{j+2} overwrites S[j&1]
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
-
-      if (j >= 1) accumulate(j - 1, alpha_prev);
-      alpha_prev = alpha;
-    }
-    accumulate(nb - 1, alpha_prev);
-
-    // finalize: normalise, stage this warp's 32 rows in its slice of sP (free: the last PV MMA has
-    // completed), then write whole 128-byte rows: lane = (row % 4, 16-byte chunk)
-    const float inv = 1.f / l_run;               // l == 0 (all keys masked) -> NaN, as torch
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      uint4 u;
-      u.x = pack_bf16x2(o[8 * ch] * inv, o[8 * ch + 1] * inv);
-      u.y = pack_bf16x2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv);
-      u.z = pack_bf16x2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv);
-      u.w = pack_bf16x2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv);
-      *reinterpret_cast<uint4*>(sP + att_swz(row, ch)) = u;
-    }
-    __syncwarp();
-    const int rr = lane >> 3, cc = lane & 7;
-    bf16* ob = out + (static_cast<int64_t>(b) * Lq + q0 + quarter * 32) * ldo + h * 64 + cc * 8;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + rr;
-      if (q0 + quarter * 32 + rl < Lq)
-        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(rl) * ldo) =
-            *reinterpret_cast<const uint4*>(sP + att_swz(quarter * 32 + rl, cc));
     }
   }
 
@@ -275,7 +332,7 @@ extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int
     TAN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
     attr_set = true;
   }
-  dim3 grid((Lq + kAttBQ - 1) / kAttBQ, H, B);
+  dim3 grid(H, B);
   return launch_pdl(attention_kernel, grid, dim3(kAttThreads), kAttSmem, static_cast<cudaStream_t>(stream), 1, tmQ,
                     tmK, tmV, key_padding_mask, static_cast<bf16*>(out), ldo, Lq, Lk);
 }

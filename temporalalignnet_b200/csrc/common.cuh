@@ -113,30 +113,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// try_wait suspends the thread in hardware until the phase completes or the suspend-time hint (ns) elapses, so
+// a waiting warp does not burn issue slots of its SM sub-partition (measured on the first version, whose
+// un-hinted waits re-issued every ~50 cycles: ~20 % of all executed instructions of the fused similarity
+// kernel were spin-loop overhead of the producer / MMA warps, profiles/r01c_prof_sim).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
 
 // Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU box.
-// ~4 s at 2 GHz; a healthy wait is microseconds.
-#ifndef TAN_MBAR_TIMEOUT_CYCLES
-#define TAN_MBAR_TIMEOUT_CYCLES (8ll << 30)
+// Each failed try_wait may suspend for up to the hint (10 ms): ~4 s in total; a healthy wait is microseconds.
+#ifndef TAN_MBAR_TIMEOUT_TRIES
+#define TAN_MBAR_TIMEOUT_TRIES 400
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  int tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > TAN_MBAR_TIMEOUT_CYCLES) __trap();
+    // the hint is an upper bound the hardware may undercut: trap only when both many tries AND ~4 s have passed
+    if (++tries > TAN_MBAR_TIMEOUT_TRIES && clock64() - t0 > (8ll << 30)) __trap();
   }
 }
 
@@ -341,6 +347,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+
+// The store counterpart: thread `lane` writes row (lane base + lane), columns [col, col+32).
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B), 8-row
 // swizzle atoms stacked every 1024 B (SBO), LBO unused for swizzled K-major (encoded 1),

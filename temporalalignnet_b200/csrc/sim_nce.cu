@@ -101,7 +101,7 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&rc)[32], uint32_t okm
 //
 // Task = one 256-frame row block of one (clip, stage) segment x one chunk of column tiles.  Each CTA of the
 // pair keeps its 128 frames x d (<= 512) bf16 = up to 128 KB in shared memory for the whole task and streams
-// only its half (128 rows) of every 256-column text tile through a 5-stage ring: 16 KB per 64-wide K block
+// only its half (128 rows) of every 256-column text tile through a 4-stage ring: 16 KB per 64-wide K block
 // for a 128 x 256 x 64 MMA share, i.e. half the L2->SM bytes of the streaming kernel (which was measured
 // operand-feed bound at ~7.3 TB/s chip-wide, profiles/r01b_prof_sim).
 //
@@ -115,12 +115,13 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&rc)[32], uint32_t okm
 //   warps 4-11  epilogue: warp (quarter, half) owns 32 frames x 128 columns of each tile
 // ---------------------------------------------------------------------------------------------
 constexpr int kSfThreads = 384;
-constexpr int kSfStages = 5;
+constexpr int kSfStages = 4;
 constexpr int kSfMaxKB = 8;
 constexpr int kSfABytes = kSfMaxKB * kG2ABytes;             // 128 KB
 constexpr int kSfRingBytes = kSfStages * kG2BBytes;         // 80 KB
 constexpr int kSfColBytes = 2 * 4 * 2 * 256 * 4;            // [buffer][quarter][all,pos][256] fp32 = 16 KB
-constexpr int kSfSmem = kSfABytes + kSfRingBytes + kSfColBytes + 1024 /*barriers*/ + 1024 /*alignment*/;
+constexpr int kSfBiasBytes = 2 * 256 * 4;                   // [buffer][256] exponent bias of the tile's columns
+constexpr int kSfSmem = kSfABytes + kSfRingBytes + kSfColBytes + kSfBiasBytes + 1024 /*barriers*/ + 1024 /*alignment*/;
 static_assert(kSfSmem <= 232448, "shared memory budget exceeded");
 
 struct SimFused {
@@ -141,7 +142,8 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSfABytes;
   float* scol = reinterpret_cast<float*>(smem + kSfABytes + kSfRingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSfABytes + kSfRingBytes + kSfColBytes);
+  float* sbias = reinterpret_cast<float*>(smem + kSfABytes + kSfRingBytes + kSfColBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSfABytes + kSfRingBytes + kSfColBytes + kSfBiasBytes);
   uint64_t* a_full = bars;                           // [8]  (leader's are used)
   uint64_t* a_empty = bars + kSfMaxKB;               // [8]
   uint64_t* b_full = bars + 2 * kSfMaxKB;            // [stages] (leader's are used)
@@ -269,6 +271,15 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t acc_phase = 0;
     int buf = 0;
     auto sc = [&](int b, int q, int which, int col) -> float& { return scol[((b * 4 + q) * 2 + which) * 256 + col]; };
+    // Exponent bias of a tile's 256 columns: -1/0.07 (log2 domain) for real sentences, -inf for padded ones and
+    // the zero padding beyond C, so e = exp2(cos * k + bias) needs no per-element predicate.  Double buffered
+    // like the column staging: the next tile's vector is written before the end-of-tile barrier.
+    auto fill_bias = [&](int b, int tn) {
+      const int col = tn * kG2BN + tid;
+      sbias[b * 256 + tid] = (col < c.g.C && c.col_valid[col] != 0) ? -kExpScale : -INFINITY;
+    };
+    if (pair_id < num_tasks) fill_bias(0, (pair_id % p.col_chunks) * p.tiles_per_chunk);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int task = pair_id; task < num_tasks; task += num_pairs) {
       const int pm = task / p.col_chunks, ck = task % p.col_chunks;
       const int seg = pm / c.seg_tiles, i = pm % c.seg_tiles;
@@ -315,12 +326,24 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sc(buf, quarter, 1, cj) = 0.f;
             continue;
           }
-          const int mycol = col0 + lane;
-          const bool my_ok = mycol < c.g.C && c.col_valid[mycol] != 0;
-          const uint32_t okmask = __ballot_sync(0xffffffffu, my_ok);
           const bool has_pos = col0 < x.pos_c1 && col0 + 32 > x.pos_c0;       // warp-uniform
           float e[32];
-          chunk_exp(rc, okmask, x, col0, has_pos, e);
+          if (x.all_rows && !(has_pos && x.any_kill)) {
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + buf * 256 + half * 128 + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];                 // same address in every lane: one broadcast read per 4 columns
+              e[4 * j + 0] = fast_exp2(fmaf(__uint_as_float(rc[4 * j + 0]), kExpScale, bb.x));
+              e[4 * j + 1] = fast_exp2(fmaf(__uint_as_float(rc[4 * j + 1]), kExpScale, bb.y));
+              e[4 * j + 2] = fast_exp2(fmaf(__uint_as_float(rc[4 * j + 2]), kExpScale, bb.z));
+              e[4 * j + 3] = fast_exp2(fmaf(__uint_as_float(rc[4 * j + 3]), kExpScale, bb.w));
+            }
+          } else {                                   // ragged last row block / killed frames: predicated path
+            const int mycol = col0 + lane;
+            const bool my_ok = mycol < c.g.C && c.col_valid[mycol] != 0;
+            const uint32_t okmask = __ballot_sync(0xffffffffu, my_ok);
+            chunk_exp(rc, okmask, x, col0, has_pos, e);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) row_all += e[j];
           float cpos = 0.f;
@@ -339,7 +362,15 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           sc(buf, quarter, 1, cj) = cpos;
         }
         // combine the four quarters in a fixed order (deterministic) and publish this CTA tile's column partials;
-        // the staging buffer alternates, so one barrier per tile orders writes against the previous reads
+        // the staging buffers alternate, so one barrier per tile orders writes against the previous reads
+        {
+          int tn_next = tn + 1;
+          if (tn_next >= tn1) {
+            const int task_next = task + num_pairs;
+            tn_next = task_next < num_tasks ? (task_next % p.col_chunks) * p.tiles_per_chunk : -1;
+          }
+          if (tn_next >= 0) fill_bias(buf ^ 1, tn_next);
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int j = tid; j < 2 * 256; j += 256) {
           const int which = j >> 8, cj = j & 255;
@@ -641,7 +672,11 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, int clips_p
     const int col = col0 + j;
     okbits |= (col < c.g.C && c.col_valid[col] != 0) ? (1u << j) : 0u;
   }
-  const bool slab_all_ok = __all_sync(0xffffffffu, okbits == 0xffu) && aligned;
+  // exponent bias per owned column: -1/0.07 (log2 domain) or -inf for padded sentences -> no predicates in the lean loop
+  float bias[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bias[j] = ((okbits >> j) & 1u) ? -kExpScale : -INFINITY;
+  const bool slab_aligned = __all_sync(0xffffffffu, aligned);
   float call[8], cpos[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { call[j] = 0.f; cpos[j] = 0.f; }
@@ -658,8 +693,8 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, int clips_p
     const int64_t pitch = static_cast<int64_t>(c.g.C) * (F32 ? 4 : 2);
     for (int t0 = warp * kNceRows; t0 < c.g.T; t0 += kNceWarps * kNceRows) {
       float ra[kNceRows], rp[kNceRows];
-      if (slab_all_ok && !slab_has_pos && t0 + kNceRows <= c.g.T) {
-        // ---- lean path: no masks, no positives
+      if (slab_aligned && !slab_has_pos && t0 + kNceRows <= c.g.T) {
+        // ---- lean path: full rows, no positives in this slab
         uint4 raw[kNceRows][F32 ? 2 : 1];
 #pragma unroll
         for (int i = 0; i < kNceRows; ++i) {
@@ -674,7 +709,7 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, int clips_p
           float sum = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float e = fast_exp2(fmaf(x[j], kExpScale, -kExpScale));
+            const float e = fast_exp2(fmaf(x[j], kExpScale, bias[j]));
             call[j] += e;
             sum += e;
           }

@@ -1,10 +1,9 @@
 """`get_loss` and helpers with the reference's signatures (train/loss.py), computed by the fused
 similarity + MIL-NCE kernels of libtan_b200.so.
 
-Supported configuration (this round): `args.model in ('init', 'cotrain')` with `sim='cos'`,
-`learn_agreement=0`, `loss_threshold=0`, `use_alignability_head=0` -- the `--model init` recipe
-(train/readme.md:10).  The self-labelling / threshold / BCE branches (train/loss.py:88-229,
-:277-357; BASELINE config 5) raise NotImplementedError instead of silently computing something else.
+Supported: `args.model in ('init', 'cotrain')`, `sim='cos'`, and every loss flag of the reference:
+`learn_agreement` with `temporal_agreement_type in ('i', 'u', 'keep', 'keep-joint')` (train/loss.py:88-229),
+`loss_threshold` (:277-304) and `use_alignability_head` (:306-357; BASELINE config 5).
 
 Closed form (verified bit-exact against the reference on CPU by the oracle tests):
 with z = logits / 0.07, valid columns = real sentences, positives = same clip and start <= t < end,
@@ -135,17 +134,18 @@ def gather_text_features(tfeat: torch.Tensor, shared_text: bool, dist) -> torch.
 
 
 def finish_loss(row_sums: torch.Tensor, col_sums: torch.Tensor, dist, T: int, reduce_fn=None, row_sel=None,
-                col_sel=None) -> torch.Tensor:
-    """Exp-sums -> loss_x.  row_sums [2, R_local], col_sums [2, S, C] (partial over the local rows).
-    Distributed: column sums add across ranks (fixed-shift exp sums); row terms are reduced locally and
-    their (sum, count) all-reduced, so every rank returns the global-batch loss."""
+                col_sel=None, reduce_cols: bool = True) -> torch.Tensor:
+    """Exp-sums -> loss_x.  row_sums [2, R_local], col_sums [2, S, C] (partial over the local rows unless
+    reduce_cols is False).  Distributed: column sums add across ranks (fixed-shift exp sums); row terms are
+    reduced locally and their (sum, count) all-reduced, so every rank returns the global-batch loss."""
     reduce_fn = ops.nce_reduce if reduce_fn is None else reduce_fn
     out4 = torch.zeros(4, dtype=torch.float64, device=row_sums.device)
     S, C = col_sums.shape[1], col_sums.shape[2]
     if dist is None:
         reduce_fn(row_sums, col_sums, out4, S, T, C, row_sel, col_sel)
     else:
-        dist.all_reduce(col_sums)
+        if reduce_cols:
+            dist.all_reduce(col_sums)
         reduce_fn(row_sums, col_sums, out4, S, T, C, row_sel, col_sel)   # cols now global, identical on every rank
         rows = out4[:2].clone()
         dist.all_reduce(rows)
@@ -153,8 +153,9 @@ def finish_loss(row_sums: torch.Tensor, col_sums: torch.Tensor, dist, T: int, re
     return nce_stats_to_loss(out4)
 
 
-def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
-    """loss_x for one model's logits (LazyLogits -> fused kernel; tensor -> streaming kernel)."""
+def nce_sums_one_model(logits, nce: NceInputs, shard: bool):
+    """(row_sums [2, B_loc*S*T], col_sums [2, S, C] summed over ALL ranks' rows, T) for one model's logits
+    (LazyLogits -> fused kernel; tensor -> streaming kernel)."""
     dist = _dist() if shard else None
     if isinstance(logits, LazyLogits):
         vfeat, tfeat = logits.vfeat, logits.tfeat
@@ -186,34 +187,199 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
         col_sums = torch.empty(2, S, C, dtype=torch.float32, device=dev)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
         ops.nce_from_logits(x, g, nce.posbits, nce.col_valid, row_sums, col_sums, ws, row_kill=nce.row_kill)
-    return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel)
+    if dist is not None:
+        dist.all_reduce(col_sums)
+    return row_sums, col_sums, T
+
+
+def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
+    """loss_x for one model's logits."""
+    dist = _dist() if shard else None
+    row_sums, col_sums, T = nce_sums_one_model(logits, nce, shard)
+    return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel, reduce_cols=False)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers of the agreement / threshold / alignability branches: tiny [B*N]-sized device vectors, no host sync
+# ------------------------------------------------------------------------------------------------
+def _gather_flat(x: torch.Tensor, dist) -> torch.Tensor:
+    """[B_loc*N] per rank -> [B*N] in global column order (rank-major)."""
+    x = x.contiguous().view(-1)
+    if dist is None:
+        return x
+    out = torch.empty(dist.get_world_size() * x.numel(), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x)
+    return out
+
+
+def masked_quantile(x: torch.Tensor, valid: torch.Tensor, q: float) -> torch.Tensor:
+    """torch.quantile(x[valid], q) (linear interpolation) without the boolean-index host sync."""
+    xs, _ = torch.sort(torch.where(valid, x.float(), torch.full_like(x, float("inf"), dtype=torch.float32)))
+    m1 = (valid.sum() - 1).clamp(min=0)
+    pos = q * m1.to(torch.float32)
+    lo = pos.floor()
+    w = pos - lo
+    lo_i = lo.long()
+    hi_i = torch.minimum(lo_i + 1, m1)
+    a, b = xs[lo_i], xs[hi_i]
+    return torch.where(w > 0, a + (b - a) * w, a)
+
+
+def _masked_standardise(x: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+    """(x - mean) / std (unbiased) over the valid entries (train/loss.py:281,:283)."""
+    v = valid.float()
+    m = v.sum()
+    mean = (x * v).sum() / m
+    var = (((x - mean) ** 2) * v).sum() / (m - 1)
+    return (x - mean) / var.sqrt()
+
+
+def _own_last_stage(lg, B: int, T: int, N: int, b_off: int) -> torch.Tensor:
+    """Own-clip cosines of the LAST stage [B_loc, T, N] fp32 (torch.diagonal(...)[:, -1], train/loss.py:92-105)."""
+    if isinstance(lg, LazyLogits):
+        Bv, S, Tv, d = lg.vfeat.shape
+        return ops.own_clip_sim(lg.vfeat, lg.tfeat, lg.shared_text, Bv, S, Tv, N, d, s_first=S - 1, s_count=1)[:, 0]
+    idx = torch.arange(B, device=lg.device)
+    return lg.detach()[idx, -1, :, b_off + idx, :].float().contiguous()
+
+
+def _pack_bits(flags_bn: torch.Tensor) -> torch.Tensor:
+    """[B, N] bool -> [B, W] int32 words (bit n % 32 of word n / 32)."""
+    B, N = flags_bn.shape
+    W = (N + 31) // 32
+    f = torch.zeros(B, W * 32, dtype=torch.int64, device=flags_bn.device)
+    f[:, :N] = flags_bn.to(torch.int64)
+    words = (f.view(B, W, 32) << torch.arange(32, device=f.device, dtype=torch.int64)).sum(-1)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
 
 
 def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding_mask, logits, args,
              abs_text_pos=None, shard_batch: Optional[bool] = None):
-    """train/loss.py:55-422 for the `--model init` recipe.  Same arguments and returned keys
-    ('loss', 'loss-dual', 'loss-joint'); every value supports `.item()` (train/main.py:127).
+    """train/loss.py:55-422.  Same arguments and returned keys ('loss', 'loss-dual', 'loss-joint' and, with the
+    respective flags, 'confidence-ratio', 'iou-threshold', 'loss-dual-all', 'loss-joint-all', 'loss-total',
+    'loss-joint-bce', 'alignability_top1'); every value supports `.item()` (train/main.py:127).
 
-    shard_batch (extension): when torch.distributed is initialised with world_size > 1, each rank
-    passes its LOCAL clips and the contrastive matrix spans the global batch (text features and
-    targets are all-gathered, column sums all-reduced).  Default: on iff a process group exists."""
+    The [B,S,T,B,N] passes run in the fused similarity+NCE kernel (or the streaming kernel for plain tensors);
+    agreement self-labelling (--learn_agreement) runs on the own-clip blocks (tan_own_clip_sim, tan_agree_scan,
+    tan_agree_targets); what remains in torch are elementwise / sort operations on [B*N]-sized vectors
+    (quantiles, standardisation, the BCE of the alignability head), without host synchronisation.
+
+    shard_batch (extension): when torch.distributed is initialised with world_size > 1, each rank passes its
+    LOCAL clips and the contrastive matrix, the quantiles and the BCE span the global batch.  Default: on iff a
+    process group exists."""
     model = getattr(args, "model", "init")
     if model not in ("init", "cotrain"):
         raise TanError(f"unknown args.model {model!r}")
     if getattr(args, "sim", "cos") != "cos":
         raise NotImplementedError("only sim='cos' (the reference default) is implemented")
-    if getattr(args, "learn_agreement", 0) or getattr(args, "loss_threshold", 0) > 0 or \
-            getattr(args, "use_alignability_head", 0):
-        raise NotImplementedError("learn_agreement / loss_threshold / alignability-head losses "
-                                  "(train/loss.py:88-229,:277-357) are not implemented in this round")
+    learn = bool(getattr(args, "learn_agreement", 0))
+    thr = float(getattr(args, "loss_threshold", 0.0) or 0.0)
+    head = bool(getattr(args, "use_alignability_head", 0))
+    kind = getattr(args, "temporal_agreement_type", "keep")
+    if learn and kind not in ops.AGREE_KINDS:
+        raise TanError(f"unknown temporal_agreement_type {kind!r}")
     logits_dual, logits_joint = logits['logits_dual'], logits['logits_joint']
     B, T, _ = video_seq.shape
     N = text_embed.shape[1]
     device = logits_dual.device
     shard = (_dist() is not None) if shard_batch is None else bool(shard_batch)
+    dist = _dist() if shard else None
     nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard)
-    loss_dual = nce_loss_one_model(logits_dual, nce, shard)
-    loss_joint = nce_loss_one_model(logits_joint, nce, shard)
-    loss_dict = {'loss-dual': loss_dual.detach(), 'loss-joint': loss_joint.detach()}
-    loss_dict['loss'] = (loss_dual + loss_joint) / 2
+    loss_dict = {}
+    if not (learn or thr > 0 or head):
+        loss_dual = nce_loss_one_model(logits_dual, nce, shard)
+        loss_joint = nce_loss_one_model(logits_joint, nce, shard)
+        loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
+        loss_dict['loss'] = (loss_dual + loss_joint) / 2
+        return loss_dict
+
+    tpm_b = text_padding_mask.to(device).bool().view(B, N)
+    tpm_u8 = tpm_b.to(torch.uint8).contiguous()
+    vpm_u8 = None
+    if video_padding_mask is not None:
+        vpm_u8 = video_padding_mask.to(device).bool().to(torch.uint8).contiguous()
+    valid_g = nce.col_valid.bool()                                           # [C] global
+    md = mj = None
+    if learn:
+        # ---- agreement self-labelling (train/loss.py:88-229) -------------------------------------
+        if model == "cotrain":
+            src_d, src_j = logits['ema-logits_dual'], logits['ema-logits_joint']
+        else:
+            src_d, src_j = logits_dual, logits_joint
+        fill = model != "cotrain"          # the reference fills the loss logits in place only in `init` mode
+        own_j = _own_last_stage(src_j, B, T, N, nce.b_off)
+        own_d = _own_last_stage(src_d, B, T, N, nce.b_off)
+        win_j, mean_j, max_j = ops.agree_scan(own_j, nce.posbits, vpm_u8, tpm_u8, B, T, N, fill_max=fill)
+        win_d, mean_d, max_d = ops.agree_scan(own_d, nce.posbits, vpm_u8, tpm_u8, B, T, N, fill_max=fill)
+        inter = (torch.minimum(win_j[..., 1], win_d[..., 1]) - torch.maximum(win_j[..., 0], win_d[..., 0])).clamp(min=0)
+        union = (win_j[..., 1] - win_j[..., 0]) + (win_d[..., 1] - win_d[..., 0]) - inter
+        iou = inter.float() / union.float().clamp(min=1e-5)
+        mean_d_g, mean_j_g = _gather_flat(mean_d, dist), _gather_flat(mean_j, dist)
+        q_d = masked_quantile(mean_d_g, valid_g, 0.3)
+        q_j = masked_quantile(mean_j_g, valid_g, 0.3)
+        conf_iou = iou >= 0.5
+        conf = (mean_d >= q_d) & (mean_j >= q_j) & conf_iou
+        replace = conf if kind in ("i", "u") else conf_iou
+        nce.posbits = ops.agree_targets(nce.posbits, win_j, win_d, replace.to(torch.uint8).contiguous(), B, T, N, kind)
+        if fill and vpm_u8 is not None:
+            nce.row_kill = vpm_u8
+        conf_g = _gather_flat(conf, dist)
+        loss_dict['confidence-ratio'] = (conf_g & valid_g).float().sum() / valid_g.float().sum()
+        loss_dict['iou-threshold'] = torch.tensor(0.5, device=device)
+        if fill:
+            md, mj = max_d, max_j
+    rs_d, cs_d, _ = nce_sums_one_model(logits_dual, nce, shard)
+    rs_j, cs_j, _ = nce_sums_one_model(logits_joint, nce, shard)
+    loss_dual = finish_loss(rs_d, cs_d, dist, T, reduce_cols=False)
+    loss_joint = finish_loss(rs_j, cs_j, dist, T, reduce_cols=False)
+    loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
+    loss_th = None
+    loss_bce = None
+    if thr > 0 or head:
+        # ---- keep the most alignable sentences (train/loss.py:277-304) -----------------------------
+        if md is None:
+            own_d = _own_last_stage(logits_dual, B, T, N, nce.b_off)
+            own_j = _own_last_stage(logits_joint, B, T, N, nce.b_off)
+            _, _, md = ops.agree_scan(own_d, nce.posbits, vpm_u8, tpm_u8, B, T, N, fill_max=False)
+            _, _, mj = ops.agree_scan(own_j, nce.posbits, vpm_u8, tpm_u8, B, T, N, fill_max=False)
+        md_g, mj_g = _gather_flat(md, dist), _gather_flat(mj, dist)
+        metric = -(_masked_standardise(md_g, valid_g) + _masked_standardise(mj_g, valid_g))
+        keep_g = (metric <= masked_quantile(metric, valid_g, thr)) & valid_g
+        if thr > 0:
+            loss_dict['loss-dual-all'], loss_dict['loss-joint-all'] = loss_dual.detach(), loss_joint.detach()
+            keep_loc = keep_g.view(-1, N)[nce.b_off:nce.b_off + B]
+            row_sel = ((nce.posbits & _pack_bits(keep_loc)[:, None, :]) != 0).any(-1).to(torch.uint8).contiguous()
+            col_sel = keep_g.to(torch.uint8).contiguous()
+            loss_dual_th = finish_loss(rs_d, cs_d, dist, T, row_sel=row_sel, col_sel=col_sel, reduce_cols=False)
+            loss_joint_th = finish_loss(rs_j, cs_j, dist, T, row_sel=row_sel, col_sel=col_sel, reduce_cols=False)
+            loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual_th.detach(), loss_joint_th.detach()
+            loss_th = (loss_dual_th + loss_joint_th) / 2
+        if head:
+            # ---- alignability BCE (train/loss.py:306-357) ------------------------------------------
+            label = torch.full_like(md_g, 2.0)
+            qd5, qj5 = masked_quantile(md_g, valid_g, 0.5), masked_quantile(mj_g, valid_g, 0.5)
+            label = torch.where((md_g > qd5) & (mj_g > qj5), torch.ones_like(label), label)
+            label = torch.where((md_g < qd5) & (mj_g < qj5), torch.zeros_like(label), label)
+            if abs_text_pos is not None:
+                centre = _gather_flat(abs_text_pos.to(device).float().mean(-1), dist)
+                label = torch.where((centre < 0.2) | (centre > 0.8), torch.zeros_like(label), label)
+            has_pos = cs_d[1].amax(0) > 0                                   # real sentences with a positive (global)
+            xj = _gather_flat(logits['joint_logits_alignability'][:, 2, :, 0].float(), dist)
+            sel = ((label != 2.0) & valid_g & has_pos).float()
+            n_sel = sel.sum()
+            y = torch.where(label == 1.0, torch.ones_like(label), torch.zeros_like(label))
+            pw = 1.0 / ((y * sel).sum() / n_sel) - 1.0
+            sp = torch.nn.functional.softplus
+            loss_bce = ((pw * y * sp(-xj) + (1 - y) * sp(xj)) * sel).sum() / n_sel
+            loss_dict['loss-joint-bce'] = loss_bce.detach()
+            loss_dict['alignability_top1'] = ((((xj > 0).float() == y).float()) * sel).sum() / n_sel
+    nce_weight = 0.0 if getattr(args, "optim_policy", "default") == "bce" else 1.0
+    if thr > 0:
+        loss_dict['loss-total'] = ((loss_dual + loss_joint) / 2).detach()
+        loss = loss_th
+    else:
+        loss = (loss_dual + loss_joint) / 2
+    if head:
+        loss = loss * nce_weight + loss_bce
+    loss_dict['loss'] = loss
     return loss_dict

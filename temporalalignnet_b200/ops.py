@@ -228,3 +228,52 @@ def nce_reduce(row_sums, col_sums, out4_f64, S: int, T: int, C_: int, row_sel=No
     check(lib().tan_nce_reduce(_ptr(row_sums), R, S, T, _ptr(row_sel), _ptr(col_sums), SC, C_, _ptr(col_sel),
                                out4_f64.data_ptr(), _stream()), "tan_nce_reduce")
     _launches += 1
+
+
+def own_clip_sim(vfeat, tfeat, shared_text: bool, B: int, S: int, T: int, N: int, d: int, s_first: int = 0,
+                 s_count: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tan_own_clip_sim -> fp32 [B, s_count, T, N] own-clip cosine blocks."""
+    global _launches
+    s_count = S - s_first if s_count is None else s_count
+    if out is None:
+        out = torch.empty(B, s_count, T, N, dtype=torch.float32, device=vfeat.device)
+    if _skip("own_clip_sim", 2.0 * B * s_count * T * N * d):
+        return out
+    check(lib().tan_own_clip_sim(vfeat.data_ptr(), tfeat.data_ptr(), 0 if shared_text else B * N * d, B, S, T, N, d,
+                                 s_first, s_count, out.data_ptr(), _stream()), "tan_own_clip_sim")
+    _launches += 1
+    return out
+
+
+def agree_scan(own, posbits, vpm_u8, tpm_u8, B: int, T: int, N: int, fill_max: bool):
+    """tan_agree_scan -> (win [B,N,2] int32, mean_logit [B,N], max_logit [B,N])."""
+    global _launches
+    dev = own.device
+    win = torch.empty(B, N, 2, dtype=torch.int32, device=dev)
+    mean_logit = torch.empty(B, N, dtype=torch.float32, device=dev)
+    max_logit = torch.empty(B, N, dtype=torch.float32, device=dev)
+    if _skip("agree", float(B * T * N), 2):
+        return win, mean_logit, max_logit
+    _need(own, torch.float32, "agree_scan.own")
+    ws = torch.empty(int(lib().tan_agree_scan_workspace_bytes(B, T, N)), dtype=torch.uint8, device=dev)
+    check(lib().tan_agree_scan(own.data_ptr(), posbits.data_ptr(), _ptr(vpm_u8), tpm_u8.data_ptr(), B, T, N,
+                               int(bool(fill_max)), win.data_ptr(), mean_logit.data_ptr(), max_logit.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream()), "tan_agree_scan")
+    _launches += 2
+    return win, mean_logit, max_logit
+
+
+AGREE_KINDS = {"i": 0, "u": 1, "keep": 2, "keep-joint": 3}
+
+
+def agree_targets(old_posbits, win_joint, win_dual, replace_u8, B: int, T: int, N: int, kind: str) -> torch.Tensor:
+    """tan_agree_targets -> new packed target bits [B, T, W]."""
+    global _launches
+    out = torch.empty_like(old_posbits)
+    if _skip("agree", float(B * T)):
+        return out
+    check(lib().tan_agree_targets(old_posbits.data_ptr(), win_joint.data_ptr(), win_dual.data_ptr(),
+                                  replace_u8.data_ptr(), B, T, N, AGREE_KINDS[kind], out.data_ptr(), _stream()),
+          "tan_agree_targets")
+    _launches += 1
+    return out

@@ -110,6 +110,11 @@ class TanStepRunner:
         preparation whenever the GPU runs dry."""
         shard, self.shard = self.shard, False        # no collectives inside these measurement graphs
         graphs_on, self.model._graphs_on = self.model._graphs_on, False
+        nce = self.nce
+        if shard:                                    # local columns only: the same kernels at the local geometry
+            lo = nce.b_off * nce.N
+            self.nce = loss_mod.NceInputs(nce.posbits, nce.col_valid[lo:lo + self.B * nce.N].contiguous(), nce.N, nce.T,
+                                          0, self.B)
         try:
             with ops.only_class(name) as acc:
                 self._step_kernels()                 # eager dry run: allocations
@@ -120,6 +125,7 @@ class TanStepRunner:
                     self._step_kernels()
         finally:
             self.shard = shard
+            self.nce = nce
             self.model._graphs_on = graphs_on
         g.replay()
         torch.cuda.synchronize()

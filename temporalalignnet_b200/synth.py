@@ -117,24 +117,30 @@ def make_batch(B: int, T: int, N: Optional[int] = None, d_in: int = 1024, text_d
 
 def make_logit_case(B: int, S: int, T: int, N: int, seed: int = 888, tag: str = "", pad_video_every: int = 0) -> dict:
     """Synthetic cosine logits [B,S,T,B,N] for loss-only parity cases (no model): uniform noise in
-    [-0.3, 0.3] plus, in every own-clip block, one bump of 2-5 frames per sentence (0.4-0.45; usually at the same place
-    for the dual and the joint model), so that the
-    self-labelling argmax of train/loss.py:136 is decisive (near-ties flip with the summation order).
+    [-0.1, 0.1] plus, in every own-clip block, one sloped bump per sentence (peak 0.45, +-10 frames wide, wider
+    than any sentence; usually at the same place for the dual and the joint model), so that every candidate
+    window of the self-labelling scan (train/loss.py:133-136) trades frames of significant probability and
+    its argmax is decisive -- on a flat profile near-ties flip with the summation order.
     Also EMA logits, alignability-head logits, absolute text positions and a batch whose clip 0 has all N
     sentences."""
     batch = make_batch(B, T, N, seed=seed, tag=f"lc{tag}", force_full=True, pad_video_every=pad_video_every)
     r = _rng(f"logits{tag}", seed)
     out = {"batch": batch}
-    base = [[(int(r.integers(2, max(T - 6, 3))), int(r.integers(2, 6))) for _ in range(N)] for _ in range(B)]
+    # bump centres stay inside the frames that are never padded (a sentence whose evidence lies in padded
+    # frames sees constant probabilities there and its argmax is decided by rounding, in the reference too)
+    c_hi = max(T - max(T // 4, 1) - 11, 3)
+    base = [[int(r.integers(2, c_hi)) for _ in range(N)] for _ in range(B)]
+    dt = np.arange(-10, 11)
+    shape = (0.45 - np.where(dt < 0, 0.04, 0.03) * np.abs(dt)).astype(np.float32)     # asymmetric: no mirrored ties
     for k in ("logits_dual", "logits_joint", "ema-logits_dual", "ema-logits_joint"):
-        x = (r.random((B, S, T, B, N), dtype=np.float32) * 2 - 1) * 0.3
+        x = (r.random((B, S, T, B, N), dtype=np.float32) * 2 - 1) * 0.1
         for b in range(B):
             for n in range(N):
-                c, w = base[b][n]                      # the two models mostly agree (IoU >= 0.5 is exercised)
+                c = base[b][n]                         # the two models mostly agree (IoU >= 0.5 is exercised)
                 if r.random() < 0.3:
-                    c, w = int(r.integers(2, max(T - 6, 3))), int(r.integers(2, 6))
-                hi = min(c + w, T)
-                x[b, :, c:hi, b, n] += 0.4 + 0.05 * r.random(hi - c, dtype=np.float32)
+                    c = int(r.integers(2, c_hi))
+                lo, hi = max(c - 10, 0), min(c + 11, T)
+                x[b, :, lo:hi, b, n] += shape[lo - (c - 10):hi - (c - 10)] * (1.0 + 0.05 * r.random(hi - lo, dtype=np.float32))
         out[k] = x
     out["dual_logits_alignability"] = r.standard_normal((B, N, 1)).astype(np.float32)
     out["joint_logits_alignability"] = r.standard_normal((B, S, N, 1)).astype(np.float32)

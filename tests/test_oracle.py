@@ -6,9 +6,9 @@ import pytest
 import torch
 
 from oracle import tan_oracle as O
-from oracle.ref_loader import reference_available
+from oracle.ref_loader import load_reference, reference_available
 from temporalalignnet_b200 import synth
-from tests.helpers import CASES, case_inputs, load_golden, max_abs
+from tests.helpers import CASES, case_inputs, checksum, load_golden, max_abs
 
 FP32_TOL = 2e-5   # fp32 reassociation noise between two CPU evaluations of the same math
 
@@ -141,3 +141,50 @@ def test_oracle_vs_live_reference_random_pos_start():
     out = orc.forward(video, text, vpm, tpm, pos_starts=draws)
     assert max_abs(out["logits_dual"], ref["logits_dual"]) < FP32_TOL
     assert max_abs(out["logits_joint"], ref["logits_joint"]) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# every get_loss branch (agreement self-labelling, threshold, alignability BCE; train/loss.py:88-373)
+# ------------------------------------------------------------------------------------------------
+from oracle.make_golden import LOSS_CASES, loss_args  # noqa: E402
+
+
+def _loss_case(name):
+    B, S, T, N, pad, kw, use_pos = LOSS_CASES[name]
+    case = synth.make_logit_case(B, S, T, N, tag=name, pad_video_every=pad)
+    batch = case["batch"]
+    logits = {k: torch.from_numpy(v.copy()) for k, v in case.items() if k not in ("batch", "abs_text_pos")}
+    atp = torch.from_numpy(case["abs_text_pos"]) if use_pos else None
+    return case, batch, logits, atp, loss_args(**kw)
+
+
+@pytest.mark.parametrize("name", list(LOSS_CASES))
+def test_full_loss_oracle_matches_reference_fixture(name):
+    gold = load_golden("g_loss_full")
+    case, batch, logits, atp, args = _loss_case(name)
+    assert abs(checksum(case["logits_dual"]) + checksum(case["logits_joint"]) - float(gold[f"{name}/in_checksum"])) < 1e-6
+    res = O.get_loss_full(logits, batch["start"], batch["end"], batch["video_padding_mask"],
+                          batch["text_padding_mask"], args, atp)
+    keys = {k.split("/", 1)[1] for k in gold if k.startswith(name + "/") and not k.endswith("in_checksum")}
+    assert set(res) == keys
+    for k in keys:
+        ref, got = float(gold[f"{name}/{k}"]), float(res[k])
+        assert abs(got - ref) <= 1e-5 * max(abs(ref), 1e-3), (name, k, got, ref)
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference")
+@pytest.mark.parametrize("name", ["agree_keep", "all_init", "all_cotrain_bce"])
+def test_full_loss_oracle_matches_live_reference(name):
+    _, _, ref_loss = load_reference()
+    case, batch, logits, atp, args = _loss_case(name)
+    B, S, T, N = LOSS_CASES[name][:4]
+    ref = ref_loss.get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]},
+                            torch.zeros(B, T, 1), torch.zeros(B, N, 1),
+                            torch.from_numpy(batch["video_padding_mask"]).float(),
+                            torch.from_numpy(batch["text_padding_mask"]).float(),
+                            {k: v.clone() for k, v in logits.items()}, args, atp)
+    res = O.get_loss_full(logits, batch["start"], batch["end"], batch["video_padding_mask"],
+                          batch["text_padding_mask"], args, atp)
+    assert set(res) == set(ref)
+    for k in ref:
+        assert abs(float(res[k]) - float(ref[k])) <= 1e-5 * max(abs(float(ref[k])), 1e-3), (k, float(res[k]), float(ref[k]))
