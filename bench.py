@@ -209,12 +209,10 @@ def run_gpu_arm(args):
     loss_val = float(loss_t)
 
     # ---- timed region 2: end to end through the public API, from pinned host memory ---------------
-    for _ in range(2):
-        runner.step_api()
+    runner.run_api_steps(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        loss_api = runner.step_api()
+    loss_api = runner.run_api_steps(steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtan_b200.so")
+LIB_PATH = os.environ.get("TAN_LIB_PATH") or os.path.join(_HERE, "libtan_b200.so")   # (override: A/B of builds)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 TAN_OK = 0

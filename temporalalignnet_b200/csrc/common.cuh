@@ -113,11 +113,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// try_wait suspends the thread in hardware until the phase completes or the suspend-time hint (ns) elapses, so
-// a waiting warp does not burn issue slots of its SM sub-partition (measured on the first version, whose
-// un-hinted waits re-issued every ~50 cycles: ~20 % of all executed instructions of the fused similarity
-// kernel were spin-loop overhead of the producer / MMA warps, profiles/r01c_prof_sim).
+// mbarrier.try_wait suspends the thread in hardware until the phase completes or a time limit elapses.  Two
+// flavours: the plain form (short implementation-defined limit: the loop re-polls every ~50 clk, lowest wake-up
+// latency) for the latency-critical consumers (MMA issuer, softmax / epilogue warps), and the form with a
+// suspend-time hint for the TMA producers, whose waits are long and whose polling would only steal issue slots
+// from the epilogue warps of their SM sub-partition.  TAN_WAIT_HINT_ALL=1 / 0 forces one flavour everywhere
+// (A/B builds).
+#ifndef TAN_WAIT_HINT_NS
+#define TAN_WAIT_HINT_NS 0x989680u
+#endif
+#ifndef TAN_WAIT_HINT_ALL
+#define TAN_WAIT_HINT_ALL 1   // measured (same box, B=256 shapes): no flavour is slower anywhere, the hinted form is
+#endif                        // ~5 % faster on the fused similarity kernel, whose epilogue is issue-bound
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
@@ -126,24 +147,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(TAN_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
 
-// Bounded wait: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU box.
-// Each failed try_wait may suspend for up to the hint (10 ms): ~4 s in total; a healthy wait is microseconds.
-#ifndef TAN_MBAR_TIMEOUT_TRIES
-#define TAN_MBAR_TIMEOUT_TRIES 400
+// Bounded waits: a protocol bug must trap (surfacing as a CUDA error) instead of hanging the GPU box
+// (~4 s at 2 GHz; a healthy wait is microseconds).
+#ifndef TAN_MBAR_TIMEOUT_CYCLES
+#define TAN_MBAR_TIMEOUT_CYCLES (8ll << 30)
 #endif
+// latency-critical consumer wait
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if defined(TAN_WAIT_HINT_ALL) && TAN_WAIT_HINT_ALL == 1
+  if (mbar_try_wait_hint(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if (clock64() - t0 > TAN_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+#else
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  int tries = 0;
+  int spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    // the hint is an upper bound the hardware may undercut: trap only when both many tries AND ~4 s have passed
-    if (++tries > TAN_MBAR_TIMEOUT_TRIES && clock64() - t0 > (8ll << 30)) __trap();
+    if ((++spins & 1023) == 0 && clock64() - t0 > TAN_MBAR_TIMEOUT_CYCLES) __trap();
   }
+#endif
+}
+// producer wait (long, not latency critical)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if defined(TAN_WAIT_HINT_ALL) && TAN_WAIT_HINT_ALL == 0
+  mbar_wait(bar, parity);
+#else
+  if (mbar_try_wait_hint(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if (clock64() - t0 > TAN_MBAR_TIMEOUT_CYCLES) __trap();
+  }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,8 +24,11 @@ __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return row * 12
 
 template <int MODE>
 struct LinearEpi2 {
-  static constexpr int kStages = 4;
-  static constexpr int kWarpScratch = 2 * 4096;
+  // Ring depth over staging space: the MMA warp trails the TMA producer by a constant ~1.8 us (per-CTA timelines,
+  // tan_debug_set_trace), so bytes in flight pace these GEMMs: the epilogue keeps ONE 4 KB staging box per warp
+  // and the ring gets 6 stages (192 KB in flight per SM): +8 % over 4 stages on the K = 512 layers (same box).
+  static constexpr int kStages = 6;
+  static constexpr int kWarpScratch = 4096;
   struct State {
     float4 res[8];         // kModeF32: residual of the next chunk, lane = (row % 4, 16-byte column)
   };
@@ -87,10 +90,11 @@ struct LinearEpi2 {
     if (MODE == kModeF32) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint8_t* buf = ws + (c & 1) * 4096;
+        uint8_t* buf = ws;
         tmem_ld_wait();
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&rc)[32] = r[c & 1];
+        if (c > 0) __syncwarp();      // chunk c-1's read-back is complete before the box is rewritten
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b = bvec[c * 8 + j];
@@ -99,7 +103,7 @@ struct LinearEpi2 {
           if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
           *reinterpret_cast<float4*>(buf + swz128(lane, j)) = make_float4(a0, a1, a2, a3);
         }
-        __syncwarp();      // also orders chunk c-1's reads of the other buffer before chunk c+1 rewrites it
+        __syncwarp();
         const int col = col0 + 32 * c;
         const int rr = lane >> 3, cc = lane & 7;
         float* po = out_f32 + static_cast<int64_t>(row0 + rr) * ldo + col + 4 * cc;
@@ -119,11 +123,8 @@ struct LinearEpi2 {
         if (residual != nullptr && c + 1 < 4) load_res(st.res, row0, col + 32, lane);
       }
     } else {
-      if (lane == 0) tma_store_wait_read<0>();        // the previous tile's stores have drained the two boxes
-      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint8_t* buf = ws + (c >> 1) * 4096;
         tmem_ld_wait();
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&rc)[32] = r[c & 1];
@@ -137,19 +138,23 @@ struct LinearEpi2 {
           packed[2 * j] = pack_bf16x2(a0, a1);
           packed[2 * j + 1] = pack_bf16x2(a2, a3);
         }
+        if ((c & 1) == 0) {                             // the box's previous TMA store has read it out
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
         // 32 features = 64 bytes = chunks [4 * (c & 1), +4) of this row of the [32 x 64] bf16 box
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(buf + swz128(lane, 4 * (c & 1) + j)) =
+          *reinterpret_cast<uint4*>(ws + swz128(lane, 4 * (c & 1) + j)) =
               make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0 && row0 < M) {
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-          if (col0 + 64 * p < N) tma_store_2d(tmOut, ws + p * 4096, col0 + 64 * p, row0);
-        tma_store_commit();
+        if (c & 1) {                                    // box complete: 64 features of 32 tokens
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < M && col0 + 32 * (c - 1) < N) {
+            tma_store_2d(tmOut, ws, col0 + 32 * (c - 1), row0);
+            tma_store_commit();
+          }
+        }
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone is done with colvec before the next tile rewrites it

@@ -192,7 +192,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int seg = pm / c.seg_tiles, i = pm % c.seg_tiles;
         const int a_row = seg * c.g.T + i * 256 + static_cast<int>(rank) * kG2BM;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&a_empty[kb], phase ^ 1);          // the previous task's MMAs have read this block
+          mbar_wait_relaxed(&a_empty[kb], phase ^ 1);          // the previous task's MMAs have read this block
           const uint32_t full_leader = mapa_u32(smem_u32(&a_full[kb]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&a_full[kb], 2 * kG2ABytes);
           tma_load_2d_pair(smem_a + kb * kG2ABytes, &tmA, full_leader, kb * kG2BK, a_row);
@@ -214,7 +214,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int b_base = static_cast<int>((seg % c.g.S) * p.b_stage_rows) + static_cast<int>(rank) * (kG2BN / 2);
         for (int tn = tn0; tn < tn1; ++tn) {
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&b_empty[stage], phase ^ 1);
+            mbar_wait_relaxed(&b_empty[stage], phase ^ 1);
             const uint32_t full_leader = mapa_u32(smem_u32(&b_full[stage]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&b_full[stage], 2 * kG2BBytes);
             tma_load_2d_pair(smem_b + stage * kG2BBytes, &tmB, full_leader, kb * kG2BK, b_base + tn * kG2BN);

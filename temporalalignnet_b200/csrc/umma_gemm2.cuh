@@ -134,7 +134,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int a_row = pt.a_row + static_cast<int>(rank) * kG2BM;
         const int b_row = pt.b_row + static_cast<int>(rank) * (kG2BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
           if (kb == 0) trace_evt2(it < 3 ? tr : nullptr, 4 + it * 8 + 0);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
@@ -242,5 +242,11 @@ int launch_umma_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return launch_pdl(kern, dim3(2 * pairs, 1, 1), dim3(kG2Threads, 1, 1), smem, stream, 2, tmA, tmB, tmOut, tmAux,
                     epi, num_kb);
 }
+
+// Measured alternatives that did NOT pay off for the linear layers (same box, M = 65536, K = 512, N = 1536 / 2048):
+// keeping the pair's weight tile resident in shared memory (halves the TMA fill traffic; 1.08 PFLOP/s, equal to
+// this kernel with a 6-stage ring: what the fills save is lost to one-wave quantisation) and keeping the token
+// rows resident (reload stalls at every task boundary).  The fused similarity kernel (sim_nce.cu), with 32
+// column tiles per resident row block, is where residency pays (0.93 of the measured bf16 peak).
 
 }  // namespace tanb

@@ -81,6 +81,45 @@ class TanStepRunner:
         ld = loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
         return ld["loss"].item()                              # D2H read of the step's result
 
+    def run_api_steps(self, n: int) -> float:
+        """n public-API steps with the NEXT step's host->device copies issued on a copy stream while the current
+        step computes (two device staging sets, events for the hand-over) -- the device-side counterpart of the
+        reference's background batch prefetcher (utils/data_utils.py:9-47, which overlaps the host side only).
+        Every step still performs its own H2D copy from pinned memory and its own `.item()` read."""
+        dev = self.device
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [tuple(torch.empty_like(t, device=dev) for t in (self.h_video, self.h_text, self.h_vpm, self.h_tpm))
+                           for _ in range(2)]
+        main = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def issue(i):
+            slot = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(consumed[slot])            # step i-2 has finished reading this staging set
+                for dst, src in zip(self._stage[slot], (self.h_video, self.h_text, self.h_vpm, self.h_tpm)):
+                    dst.copy_(src, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        loss = float("nan")
+        issue(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue(i + 1)
+            slot = i & 1
+            main.wait_event(ready[slot])
+            video, text, vpm, tpm = self._stage[slot]
+            out = self.model(video, text, video_padding_mask=vpm, lang_padding_mask=tpm, text_timestamp=None,
+                             abs_text_pos=None)
+            ld = loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
+            consumed[slot].record(main)
+            loss = ld["loss"].item()                                  # D2H read of the step's result
+        return loss
+
     # -- device-resident step -----------------------------------------------------------------------
     def _step_kernels(self) -> torch.Tensor:
         out = self.model(self.d_video, self.d_text, video_padding_mask=self.d_vpm, lang_padding_mask=self.d_tpm)
