@@ -244,6 +244,13 @@ def run_gpu_arm(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # dram__bytes_read + dram__bytes_write per launch from the committed `ncu --set full` captures of the same
+    # shapes (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep files)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
@@ -253,23 +260,37 @@ def run_gpu_arm(args):
         lin = agg["linear"]
         lin_tf = lin[0] / (lin[1] * 1e-3) / 1e12
         kernel_ms = {k: round(v[1] / steps, 4) for k, v in agg.items()}
-        roofline = {"kernel": "umma_gemm2_kernel<LinearEpi2> (tan_linear_bf16: QKV/out/MLP/pre projections)",
+        roofline = {"kernel": "umma_gemm2_kernel<LinearEpi2> (tan_linear_bf16: QKV/out/MLP/pre projections; the "
+                              "kernel class with the largest share of the step)",
                     "bound": "tensor", "achieved": round(lin_tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": round(lin_tf / tf_peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(lin_tf / tf_peak, 4),
+                    "traffic": (traffic.get("linear") or {}).get("bytes_per_launch") if world == 1 else None,
+                    "traffic_source": (traffic.get("linear") or {}).get("source"), "peak_source": peak_src,
                     "launches_per_step": lin[2] // steps, "avg_launch_us": round(1e3 * lin[1] / max(lin[2], 1), 2),
                     "share_of_step": round(lin[1] / steps / ms_per_step, 3),
                     "how": "CUDA graph of the step's tan_linear_bf16 launches alone, CUDA events per replay, "
                            "L2 flushed between replays"}
         s_ = agg["sim_nce_fwd"]
-        extra["roofline_sim"] = {"kernel": "umma_gemm_kernel<SimEpi> (tan_sim_nce_fwd, fused mode)", "bound": "tensor",
+        extra["roofline_sim"] = {"kernel": "sim_fused_kernel + sim_reduce_partials_kernel (tan_sim_nce_fwd, fused mode: "
+                                           "the logits never reach HBM)", "bound": "tensor",
                                  "achieved": round(s_[0] / (s_[1] * 1e-3) / 1e12, 1), "peak": tf_peak,
-                                 "unit": "TFLOP/s", "frac": round(s_[0] / (s_[1] * 1e-3) / 1e12 / tf_peak, 4)}
+                                 "unit": "TFLOP/s", "frac": round(s_[0] / (s_[1] * 1e-3) / 1e12 / tf_peak, 4),
+                                 "traffic": (traffic.get("sim_nce_fwd") or {}).get("bytes_per_launch") if world == 1 else None,
+                                 "columns": "local columns only (collectives are excluded from the per-class graphs)"
+                                 if world > 1 else "global"}
         a_ = agg["attention"]
         extra["roofline_attention"] = {"kernel": "attention_kernel (tan_attention_bf16, tcgen05)", "bound": "tensor",
                                        "achieved": round(a_[0] / (a_[1] * 1e-3) / 1e12, 1), "peak": tf_peak,
                                        "unit": "TFLOP/s", "frac": round(a_[0] / (a_[1] * 1e-3) / 1e12 / tf_peak, 4),
                                        "avg_launch_us": round(1e3 * a_[1] / max(a_[2], 1), 2)}
         extra["kernel_ms_per_step"] = kernel_ms
+        # north_star's "attention / encoder path": both transformer stacks (projections, attention core, LayerNorms)
+        fl_ = runner.flops_per_clip()
+        enc_ms = (agg["linear"][1] + agg["attention"][1] + agg["layernorm"][1]) / steps
+        extra["encoder_path"] = {"flops_per_clip": fl_["pre"] + fl_["enc"] + fl_["joint"], "ms_per_step": round(enc_ms, 4),
+                                 "achieved": round((fl_["pre"] + fl_["enc"] + fl_["joint"]) * B_PER_GPU / (enc_ms * 1e-3) / 1e12, 1),
+                                 "unit": "TFLOP/s", "peak": tf_peak,
+                                 "frac": round((fl_["pre"] + fl_["enc"] + fl_["joint"]) * B_PER_GPU / (enc_ms * 1e-3) / 1e12 / tf_peak, 4)}
     fl = runner.flops_per_clip()
     extra["whole_step_tensor_frac"] = round(fl["total"] * B_PER_GPU / (ms_per_step * 1e-3) / 1e12 / tf_peak, 4)
 
@@ -332,8 +353,14 @@ def hbm_nce_roofline(runner, peaks, flush):
     nbytes = dense.numel() * 2
     hbm = float(peaks.get("hbm_gbs", 6650.0)) if peaks else 6650.0
     gbs = nbytes / (ms * 1e-3) / 1e9
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     return {"kernel": "nce_from_logits_kernel<bf16> + partial reduce (tan_nce_from_logits)", "bound": "hbm",
-            "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(gbs / hbm, 4), "traffic": None,
+            "achieved": round(gbs, 1), "peak": hbm, "unit": "GB/s", "frac": round(gbs / hbm, 4),
+            "traffic": (traffic.get("nce_from_logits") or {}).get("bytes_per_launch"),
             "bytes": nbytes, "ms": round(ms, 4)}
 
 

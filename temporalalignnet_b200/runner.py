@@ -12,6 +12,7 @@ global batch (loss.py all-gathers text features / targets and all-reduces column
 """
 from __future__ import annotations
 
+import os
 import types
 from typing import Optional
 
@@ -48,6 +49,8 @@ class TanStepRunner:
         self.model = TemporalAligner(self.E, self.D, random_pos_start=0, width=width, video_dim=video_dim)
         self.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         self.model = self.model.to(self.device)
+        if os.environ.get("TAN_TWO_STREAMS") is not None:            # A/B aid
+            self.model.two_streams = os.environ["TAN_TWO_STREAMS"] != "0"
         if self.use_model_graph:
             self.model.enable_cuda_graphs(True)
         self.batch = synth.make_batch(B_loc, T, self.N, d_in=video_dim, seed=seed, tag=f"rank{rank}")
@@ -128,10 +131,16 @@ class TanStepRunner:
         return (l_dual + l_joint) / 2
 
     def warmup(self, n=3):
-        for _ in range(n):
-            n0 = ops.launches()
+        # kernels per step, counted on one EAGER step (launches replayed from a CUDA graph do not pass through
+        # the ops wrappers; capture passes do, but are not steps)
+        graphs_on, self.model._graphs_on = self.model._graphs_on, False
+        self._step_kernels()                         # first call also casts the weights to their bf16 shadows
+        n0 = ops.launches()
+        loss = self._step_kernels()
+        self.launches_per_step = ops.launches() - n0
+        self.model._graphs_on = graphs_on
+        for _ in range(max(n - 2, 1)):
             loss = self._step_kernels()
-            self.launches_per_step = ops.launches() - n0
         torch.cuda.synchronize()
         if self.use_graph and self._graph is None:
             g = torch.cuda.CUDAGraph()
