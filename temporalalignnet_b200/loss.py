@@ -199,6 +199,46 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
     return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel, reduce_cols=False)
 
 
+def nce_losses_pair(logits_dual, logits_joint, nce: NceInputs, shard: bool):
+    """(loss_dual, loss_joint).  Sharded + fused path: the exchange of BOTH models is batched into one
+    all-gather (text features of the dual model stacked on the joint model's stages), one all-reduce (column
+    sums) and one tiny all-reduce (row sums / counts) -- the collectives are latency-bound at these sizes
+    (1-6 MB per rank), so their number, not their volume, is what a step pays for."""
+    dist = _dist() if shard else None
+    if dist is None or not (isinstance(logits_dual, LazyLogits) and isinstance(logits_joint, LazyLogits)):
+        return nce_loss_one_model(logits_dual, nce, shard), nce_loss_one_model(logits_joint, nce, shard)
+    vd, vj = logits_dual.vfeat, logits_joint.vfeat
+    td, tj = logits_dual.tfeat, logits_joint.tfeat                       # [B_loc*N, d], [Sj, B_loc*N, d]
+    B, Sd, T, d = vd.shape
+    Sj = vj.shape[1]
+    dev = vd.device
+    W = dist.get_world_size()
+    BN = td.shape[0]
+    packed = torch.cat((td[None], tj), dim=0).contiguous()               # [1 + Sj, B_loc*N, d]
+    gathered = torch.empty(W * (1 + Sj), BN, d, dtype=packed.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, packed)
+    full = gathered.view(W, 1 + Sj, BN, d).permute(1, 0, 2, 3).reshape(1 + Sj, W * BN, d).contiguous()
+    C = W * BN
+    cols = torch.empty(2 * (Sd + Sj) * C, dtype=torch.float32, device=dev)
+    cs_d, cs_j = cols[:2 * Sd * C].view(2, Sd, C), cols[2 * Sd * C:].view(2, Sj, C)
+    rs_d = torch.empty(2, B * Sd * T, dtype=torch.float32, device=dev)
+    rs_j = torch.empty(2, B * Sj * T, dtype=torch.float32, device=dev)
+    g_d = ops.sim_geom(B, Sd, T, C, nce.N, d, nce.b_off)
+    g_j = ops.sim_geom(B, Sj, T, C, nce.N, d, nce.b_off)
+    ws = torch.empty(max(ops.sim_workspace_bytes(g_d), ops.sim_workspace_bytes(g_j)), dtype=torch.uint8, device=dev)
+    ops.sim_nce_fwd(vd, full[0], 0, g_d, nce.posbits, nce.col_valid, None, rs_d, cs_d, ws, row_kill=nce.row_kill)
+    ops.sim_nce_fwd(vj, full[1:], C * d, g_j, nce.posbits, nce.col_valid, None, rs_j, cs_j, ws, row_kill=nce.row_kill)
+    dist.all_reduce(cols)
+    out8 = torch.zeros(8, dtype=torch.float64, device=dev)
+    ops.nce_reduce(rs_d, cs_d, out8[0:4], Sd, T, C, nce.row_sel, nce.col_sel)
+    ops.nce_reduce(rs_j, cs_j, out8[4:8], Sj, T, C, nce.row_sel, nce.col_sel)
+    rows = torch.cat((out8[0:2], out8[4:6]))
+    dist.all_reduce(rows)
+    loss_d = nce_stats_to_loss(torch.cat((rows[0:2], out8[2:4])))
+    loss_j = nce_stats_to_loss(torch.cat((rows[2:4], out8[6:8])))
+    return loss_d, loss_j
+
+
 # ------------------------------------------------------------------------------------------------
 # helpers of the agreement / threshold / alignability branches: tiny [B*N]-sized device vectors, no host sync
 # ------------------------------------------------------------------------------------------------
@@ -287,8 +327,7 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard)
     loss_dict = {}
     if not (learn or thr > 0 or head):
-        loss_dual = nce_loss_one_model(logits_dual, nce, shard)
-        loss_joint = nce_loss_one_model(logits_joint, nce, shard)
+        loss_dual, loss_joint = nce_losses_pair(logits_dual, logits_joint, nce, shard)
         loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
         loss_dict['loss'] = (loss_dual + loss_joint) / 2
         return loss_dict

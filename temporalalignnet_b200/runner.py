@@ -126,8 +126,7 @@ class TanStepRunner:
     # -- device-resident step -----------------------------------------------------------------------
     def _step_kernels(self) -> torch.Tensor:
         out = self.model(self.d_video, self.d_text, video_padding_mask=self.d_vpm, lang_padding_mask=self.d_tpm)
-        l_dual = loss_mod.nce_loss_one_model(out["logits_dual"], self.nce, self.shard)
-        l_joint = loss_mod.nce_loss_one_model(out["logits_joint"], self.nce, self.shard)
+        l_dual, l_joint = loss_mod.nce_losses_pair(out["logits_dual"], out["logits_joint"], self.nce, self.shard)
         return (l_dual + l_joint) / 2
 
     def warmup(self, n=3):
