@@ -39,8 +39,9 @@ constexpr int kAttKVBytes = kAttBK * 128;     // 8 KB
 #endif
 constexpr int kAttKStages = TAN_ATT_KSTAGES;
 constexpr int kAttVStages = 3;
+constexpr int kAttMaskWords = 128;            // mask bits for Lk <= 4096 (longer sequences: per-block loads)
 constexpr int kAttSmem = 2 * kAttQBytes /*Q x 2*/ + (kAttKStages + kAttVStages) * kAttKVBytes + 2 * kAttQBytes /*P x 2*/ +
-                         512 /*bars*/;
+                         256 /*bars*/ + kAttMaskWords * 4;
 static_assert(2 * (kAttSmem + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
@@ -67,6 +68,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* pv_done = bars + 20;      // [2] PV_g has completed (g & 1): P buffer free, O stable
   uint64_t* o_free = bars + 22;       // [2] count 4: the tile's O has been read out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  // key mask of the clip as bits (bit set = ignore key).  Inside the dynamic segment on purpose: a static
+  // __shared__ array would shift the 1024-aligned dynamic base without growing the allocation.
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +177,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float sl2 = 0.125f * 1.4426950408889634f;    // 1/sqrt(64) folded with log2(e)
     const uint8_t* mb = kpm != nullptr ? kpm + static_cast<int64_t>(b) * Lk : nullptr;
+    // the clip's key mask as bits, once (a per-block byte load would put a global-memory round trip on the
+    // critical path of every block: 5 % of the samples in ncu r01e)
+    const bool mask_in_smem = nb * 2 <= kAttMaskWords;
+    if (mask_in_smem) {
+      for (int wd = quarter; wd < nb * 2; wd += 4) {
+        const int key = wd * 32 + lane;
+        const bool ig = key >= Lk || (mb != nullptr && mb[key] != 0);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ig);
+        if (lane == 0) s_mask[wd] = bits;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 
     for (int qt = 0; qt < nq; ++qt) {
       const int q0 = (qt0 + qt) * kAttBQ;
@@ -186,10 +202,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         if (live) {
           // key mask of this block as two warp-uniform words (bit set = ignore key)
-          const int k0 = j * kAttBK + lane, k1 = k0 + 32;
-          const bool ig0 = k0 >= Lk || (mb != nullptr && mb[k0] != 0);
-          const bool ig1 = k1 >= Lk || (mb != nullptr && mb[k1] != 0);
-          const uint32_t w0 = __ballot_sync(0xffffffffu, ig0), w1 = __ballot_sync(0xffffffffu, ig1);
+          uint32_t w0, w1;
+          if (mask_in_smem) {
+            w0 = s_mask[2 * j];
+            w1 = s_mask[2 * j + 1];
+          } else {
+            const int k0 = j * kAttBK + lane, k1 = k0 + 32;
+            const bool ig0 = k0 >= Lk || (mb != nullptr && mb[k0] != 0);
+            const bool ig1 = k1 >= Lk || (mb != nullptr && mb[k1] != 0);
+            w0 = __ballot_sync(0xffffffffu, ig0);
+            w1 = __ballot_sync(0xffffffffu, ig1);
+          }
           uint32_t r0[32], r1[32];
           const uint32_t t_s = t_lane + (g & 1) * 64;
           tmem_ld_32x32(t_s, r0);
@@ -344,8 +367,8 @@ extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int
   // one CTA per (clip, head) when that fills the GPU (2 CTAs per SM); otherwise split the query tiles over
   // blockIdx.z so that short batches of long sequences still occupy every SM
   const int nq_total = (Lq + kAttBQ - 1) / kAttBQ;
-  const int64_t want = num_sms();                 // (a full pipeline per CTA beats twice as many short CTAs)
-  int split = static_cast<int>(want / (static_cast<int64_t>(B) * H));
+  const int64_t want = 2ll * num_sms();           // two CTAs per SM; rounding DOWN: a full pipeline per CTA beats
+  int split = static_cast<int>(want / (static_cast<int64_t>(B) * H));   // twice as many short CTAs (measured)
   if (split > nq_total) split = nq_total;
   if (split < 1) split = 1;
   const int tiles_per_cta = (nq_total + split - 1) / split;
