@@ -360,6 +360,31 @@ def test_nce_from_logits_killed_rows_and_many_clips(dtype):
     assert ((rs[1] > 0) == (row[1] > 0)).all() and ((cs[1] > 0) == (col[1] > 0)).all()
 
 
+@pytest.mark.parametrize("B_loc,b_off,B_glob,S,T,N,shared", [
+    (2, 17, 40, 2, 200, 32, False),      # few row blocks, 5 column tiles: the fused kernel splits the column sweep
+    (3, 0, 24, 1, 520, 64, True),        # 3 row blocks per segment, ragged last one; N = 64 (two target words)
+    (1, 9, 10, 3, 64, 100, False),       # sentences straddle 32-column chunks and 256-column tiles
+])
+def test_sim_nce_fwd_local_rows_global_columns(B_loc, b_off, B_glob, S, T, N, shared):
+    """The multi-GPU geometry: local rows x global columns (b_off > 0), column chunking of the resident-row
+    kernel, own-clip blocks in the middle of the column range."""
+    ops = _ops()
+    d = 512
+    v, t, start, end, valid = _sim_inputs(B_glob, S, T, N, d, 41, shared)
+    v = v[b_off:b_off + B_loc].contiguous()
+    C = B_glob * N
+    g = ops.sim_geom(B_loc, S, T, C, N, d, b_off)
+    rs = torch.empty(2, B_loc * S * T, device=DEV)
+    cs = torch.empty(2, S, C, device=DEV)
+    ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=DEV)
+    posbits = _posbits(ops, start, end, valid, B_glob, T, N, b_off, B_loc)
+    ops.sim_nce_fwd(v, t, 0 if shared else C * d, g, posbits, valid, None, rs, cs, ws)
+    _, row, col = _sim_ref(v, t, start, end, valid, B_glob, S, T, N, shared, b_off=b_off, B_loc=B_loc)
+    assert ((rs - row).abs() / row.clamp_min(1e-30)).max().item() < 1e-3
+    assert ((cs - col).abs() / col.clamp_min(1e-30)).max().item() < 1e-3
+    assert ((rs[1] > 0) == (row[1] > 0)).all() and ((cs[1] > 0) == (col[1] > 0)).all()
+
+
 def test_sim_sharded_rows_add_up():
     """Column sums are additive over row shards (the multi-GPU exchange relies on it)."""
     ops = _ops()

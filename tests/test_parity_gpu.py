@@ -132,7 +132,10 @@ def test_temporal_decoder_vs_reference_fixture():
     assert rel_fro(got, g["dec_out"]) < FEAT_RFRO
 
 
-@pytest.mark.parametrize("E,D,B,T,N,width,din", [(2, 2, 6, 96, 12, 512, 1024), (1, 2, 2, 160, 20, 768, 768)])
+@pytest.mark.parametrize("E,D,B,T,N,width,din", [
+    (2, 2, 6, 96, 12, 512, 1024), (1, 2, 2, 160, 20, 768, 768),
+    (6, 6, 16, 64, 8, 512, 1024),        # BASELINE configs[1] (E6D6, T=64, the paper shape) at 16 clips
+])
 def test_forward_and_loss_vs_oracle_fresh_inputs(E, D, B, T, N, width, din):
     """Sizes the oracle finishes in seconds; includes the width-768 / 12-head variant of config 4."""
     from oracle import tan_oracle as O
