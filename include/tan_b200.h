@@ -82,6 +82,18 @@ TAN_API int tan_linear_bf16(const void* A, int64_t lda, const void* W, int64_t l
                     const float* residual, int64_t ldr, float* out_f32, int64_t ldo_f32,
                     void* out_bf16, int64_t ldo_bf16, int M, int N, int K, int act, void* stream);
 
+/* Fused projection + residual + LayerNorm for an output width of 512 (= the model width):
+ *     x   <- x + A @ W^T + bias                 x [M, 512] fp32 (ldx), updated in place
+ *     out <- LayerNorm(x) * gamma + beta         out [M, 512] bf16 (ldo); eps = 1e-5, biased variance
+ *   A [M, K] bf16 (lda), W [512, K] bf16 (ldw), bias [512] fp32 or NULL, gamma / beta [512] fp32.
+ * Requirements: N == 512, K % 64 == 0, lda/ldw/ldo % 8 == 0, ldx % 4 == 0, 16-byte aligned bases.
+ * Replaces the attention out-projection + residual add (torch MHA out_proj reached from model/tfm_model.py:32,
+ * `x = x + attn` at :36) together with `self.ln_2(x)` at :37: the fp32 residual stream is read and written
+ * once instead of twice. */
+TAN_API int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                           float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                           int64_t ldo, int M, int N, int K, void* stream);
+
 /* ---- LayerNorm (+ positional add, scatter, L2-normalised stage features) ---------------------- */
 
 /* Row-wise LayerNorm over the last dimension with optional fused extras.  For input row r

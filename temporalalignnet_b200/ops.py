@@ -131,6 +131,23 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     _launches += 1
 
 
+def linear_res_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+                  gamma: torch.Tensor, beta: torch.Tensor, out_bf16: torch.Tensor) -> None:
+    """x += a @ w.T + bias (fp32, in place); out_bf16 = LayerNorm(x) * gamma + beta  (tan_linear_res_ln_bf16;
+    output width 512).  Counted with the linear class (flops of the GEMM)."""
+    global _launches
+    M, K = a.shape
+    N = w.shape[0]
+    if _skip("linear", 2.0 * M * N * K):
+        return
+    with _timed("linear", 2.0 * M * N * K):
+        check(lib().tan_linear_res_ln_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                                           x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                           out_bf16.data_ptr(), out_bf16.stride(0), M, N, K, _stream()),
+              "tan_linear_res_ln_bf16")
+    _launches += 1
+
+
 def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=None, add_rows: int = 0,
               L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0,
               out_f32=None, out_bf16=None, l_split: int = 0, strideA: int = 0, strideB: int = 0,

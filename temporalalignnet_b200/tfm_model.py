@@ -10,6 +10,7 @@ called.  Forward-only (inference / loss evaluation): outputs carry no autograd g
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import List, Optional
 
@@ -54,6 +55,9 @@ class _Bf16Cache:
             p = ent[3]
             if ent[0] != p._version or ent[1] != p.data_ptr():
                 self.get(p)
+
+
+FUSE_OUTPROJ_LN = os.environ.get("TAN_FUSE_OUTPROJ_LN", "1") != "0"     # A/B aid
 
 
 def _f32(p: torch.Tensor) -> torch.Tensor:
@@ -132,8 +136,13 @@ def run_encoder_stack(blocks, x: torch.Tensor, kpm_u8: Optional[torch.Tensor], B
         ops.linear(buf.xn, cache.get(blk.attn.in_proj_weight), _f32(blk.attn.in_proj_bias), out_bf16=buf.qkv)
         ops.attention(buf.qkv[:, 0:d], buf.qkv[:, d:2 * d], buf.qkv[:, 2 * d:3 * d], kpm_u8, buf.att, B, blk.n_head,
                       L, L)
-        ops.linear(buf.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), residual=x, out_f32=x)
-        ops.layernorm(x, M, d, gamma=_f32(blk.ln_2.weight), beta=_f32(blk.ln_2.bias), L_in=L, out_bf16=buf.xn)
+        if d == 512 and FUSE_OUTPROJ_LN:
+            # out-projection + residual + ln_2 in one kernel: the fp32 residual stream is read and written once
+            ops.linear_res_ln(buf.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), x,
+                              _f32(blk.ln_2.weight), _f32(blk.ln_2.bias), buf.xn)
+        else:
+            ops.linear(buf.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), residual=x, out_f32=x)
+            ops.layernorm(x, M, d, gamma=_f32(blk.ln_2.weight), beta=_f32(blk.ln_2.bias), L_in=L, out_bf16=buf.xn)
         ops.linear(buf.xn, cache.get(blk.mlp.c_fc.weight), _f32(blk.mlp.c_fc.bias), out_bf16=buf.h, act=ACT_QUICKGELU)
         ops.linear(buf.h, cache.get(blk.mlp.c_proj.weight), _f32(blk.mlp.c_proj.bias), residual=x, out_f32=x)
     if emit_final and S >= 1:

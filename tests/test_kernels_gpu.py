@@ -90,6 +90,27 @@ def test_linear_residual_in_place_and_strided_views():
     assert big[:, :d].abs().max().item() == 0 and big[:, 2 * d:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("M,K", [(256, 512), (8192, 512), (1000, 512), (300, 2048), (37, 64)])
+def test_linear_res_ln(M, K):
+    """Fused out-projection + residual + LayerNorm against torch fp32 on the bf16-rounded operands."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + K)
+    a = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(512, K, generator=g) * K ** -0.5).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(512, generator=g).to(DEV)
+    x0 = (torch.randn(M, 512, generator=g) * 1.5 + 0.3).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(512, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(512, generator=g)).to(DEV)
+    x = x0.clone()
+    out = torch.full((M, 512), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.linear_res_ln(a, w, bias, x, gamma, beta, out)
+    x_ref = x0 + a.float() @ w.float().t() + bias
+    y_ref = torch.nn.functional.layer_norm(x_ref, (512,), gamma, beta, 1e-5)
+    assert (x - x_ref).abs().max().item() < 2e-3
+    assert (out.float() - y_ref).abs().max().item() < 3e-2          # bf16 output of O(1..4) values
+    assert ((out.float() - y_ref).norm() / y_ref.norm()).item() < 4e-3
+
+
 def test_linear_rejects_bad_shapes():
     from temporalalignnet_b200 import TanError
     ops = _ops()
