@@ -94,6 +94,19 @@ TAN_API int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W, in
                            float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
                            int64_t ldo, int M, int N, int K, void* stream);
 
+/* The same with the stage-feature emission of tan_layernorm (below): additionally (or instead of `out`, which may
+ * be NULL) writes y / ||y||_2 as bf16, y = LayerNorm(x) * gamma + beta, for token r = b * L + l to
+ *     nrmA_bf16[b * strideA + l]            (l <  l_split: video tokens)
+ *     nrmB_bf16[b * strideB + l - l_split]  (l >= l_split: text tokens of the joint sequence; may be NULL if l_split == L).
+ * Requirements: as above, M % L == 0, L % 32 == 0, l_split % 32 == 0 (a warp stores 32 consecutive tokens as one
+ * TMA box).  Replaces c_proj + residual (model/tfm_model.py:37) together with the NEXT block's ln_1 (:35) -- whose
+ * output is also the previous stage's feature (:50-53) -- or with ln_video_post_enc / ln_joint_post_enc
+ * (model/tan_model.py:174,:206), and the L2 normalisation of model/tan_model.py:116-117,:136-137. */
+TAN_API int tan_linear_res_ln_stage_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                 float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                                 int64_t ldo, int M, int N, int K, int L, int l_split, void* nrmA_bf16,
+                                 int64_t strideA, void* nrmB_bf16, int64_t strideB, void* stream);
+
 /* ---- LayerNorm (+ positional add, scatter, L2-normalised stage features) ---------------------- */
 
 /* Row-wise LayerNorm over the last dimension with optional fused extras.  For input row r

@@ -38,13 +38,18 @@ struct ResLnArgs {
   const float* beta;
   float* x;          // [M, 512] fp32, in/out
   int64_t ldx;
+  int has_out;       // xn output requested
+  int emit;          // L2-normalised stage features requested (tmNA / tmNB)
+  int L, l_split;    // tokens per clip, first token of the "B" part (text tokens of the joint sequence)
+  int64_t strideA, strideB;   // destination row = b * strideA + l  (l < l_split)  or  b * strideB + (l - l_split)
 };
 
 __device__ __forceinline__ uint32_t ln_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 __global__ void __launch_bounds__(kLnThreads, 1)
 gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmOut, const ResLnArgs p) {
+                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmNA,
+                   const __grid_constant__ CUtensorMap tmNB, const ResLnArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -68,6 +73,8 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmNA);
+    tma_prefetch_desc(&tmNB);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kLnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -234,13 +241,15 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float var = fmaxf(t2 * (1.0f / kLnN) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
 
-      // ---- pass 2: xn = (x - mean) * rstd * gamma + beta -> bf16 boxes -> TMA store
+      // ---- pass 2: y = (x - mean) * rstd * gamma + beta -> bf16 boxes -> TMA store of xn; with stage emission
+      // also sum of squares of y (thread-local) and y back to TMEM for pass 3
+      float q2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (c == 7) {                                  // the accumulators are in registers: hand TMEM back
+        if (c == 7 && !p.emit) {                       // the accumulators are in registers: hand TMEM back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty), 0));
@@ -255,21 +264,72 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const float a3 = (__uint_as_float(r[4 * j + 3]) - mean) * rstd * g.w + e.w;
           packed[2 * j] = pack_bf16x2(a0, a1);
           packed[2 * j + 1] = pack_bf16x2(a2, a3);
+          if (p.emit) {
+            q2 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+            r[4 * j] = __float_as_uint(a0); r[4 * j + 1] = __float_as_uint(a1);
+            r[4 * j + 2] = __float_as_uint(a2); r[4 * j + 3] = __float_as_uint(a3);
+          }
         }
-        if ((c & 1) == 0) {                             // the box's previous TMA store has read it out
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-        }
+        if (p.emit) tmem_st_32x32(taddr + c * 32, r);
+        if (p.has_out) {
+          if ((c & 1) == 0) {                           // the box's previous TMA store has read it out
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(ws + ln_swz(lane, 4 * (c & 1) + j)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        if (c & 1) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && row0 < p.M) {
-            tma_store_2d(&tmOut, ws, col0 + 32 * (c - 1), row0);
-            tma_store_commit();
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(ws + ln_swz(lane, 4 * (c & 1) + j)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M) {
+              tma_store_2d(&tmOut, ws, col0 + 32 * (c - 1), row0);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      if (p.emit) {
+        // ---- pass 3: stage feature = y / ||y||_2 (model/tan_model.py:116-117,:136-137) -> bf16, scattered by clip
+        tmem_st_wait();
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has read the pass-1 sums
+        stats[(half * 128 + rloc) * 2] = q2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = 1.0f / sqrtf(stats[rloc * 2] + stats[(128 + rloc) * 2]);
+        const int b_clip = row0 / p.L, l0 = row0 - b_clip * p.L;          // the warp's 32 rows share clip and part
+        const bool part_a = l0 < p.l_split;
+        const int64_t dst_row = part_a ? b_clip * p.strideA + l0 : b_clip * p.strideB + (l0 - p.l_split);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (c == 7) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty), 0));
+          }
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(ws + ln_swz(lane, 4 * (c & 1) + j)) = u;
+          }
+          if (c & 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < p.M) {
+              tma_store_2d(part_a ? &tmNA : &tmNB, ws, col0 + 32 * (c - 1), static_cast<int>(dst_row));
+              tma_store_commit();
+            }
           }
         }
       }
@@ -293,22 +353,29 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 using namespace tanb;
 
-extern "C" int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
-                                      float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
-                                      int64_t ldo, int M, int N, int K, void* stream) {
+static int launch_res_ln(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, float* x,
+                         int64_t ldx, const float* gamma, const float* beta, void* out_bf16, int64_t ldo, int M,
+                         int N, int K, int L, int l_split, void* nrmA, int64_t strideA, void* nrmB, int64_t strideB,
+                         void* stream) {
   TAN_CHECK(tan_device_check());
-  if (A == nullptr || W == nullptr || x == nullptr || gamma == nullptr || beta == nullptr || out_bf16 == nullptr)
-    return set_error(TAN_ERR_ARG, "tan_linear_res_ln_bf16: null pointer");
-  if (N != kLnN) return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln_bf16: N must be 512 (N=%d)", N);
+  if (A == nullptr || W == nullptr || x == nullptr || gamma == nullptr || beta == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_linear_res_ln: null pointer");
+  const bool emit = nrmA != nullptr || nrmB != nullptr;
+  if (out_bf16 == nullptr && !emit) return set_error(TAN_ERR_ARG, "tan_linear_res_ln: no output requested");
+  if (N != kLnN) return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: N must be 512 (N=%d)", N);
   if (M <= 0 || K <= 0 || K % kG2BK != 0)
-    return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln_bf16: need M>0, K%%64==0 (M=%d K=%d)", M, K);
-  if (lda % 8 != 0 || ldw % 8 != 0 || lda < K || ldw < K || ldx % 4 != 0 || ldx < N || ldo % 8 != 0 || ldo < N ||
-      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out_bf16) & 15))
-    return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln_bf16: row pitches / alignment");
-  CUtensorMap tmA, tmB, tmOut;
+    return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: need M>0, K%%64==0 (M=%d K=%d)", M, K);
+  if (lda % 8 != 0 || ldw % 8 != 0 || lda < K || ldw < K || ldx % 4 != 0 || ldx < N ||
+      (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (out_bf16 != nullptr && (ldo % 8 != 0 || ldo < N || (reinterpret_cast<uintptr_t>(out_bf16) & 15))))
+    return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: row pitches / alignment");
+  CUtensorMap tmA, tmB, tmOut, tmNA, tmNB;
   TAN_CHECK(make_tmap_2d(&tmA, A, 2, M, K, lda, kG2BM));
   TAN_CHECK(make_tmap_2d(&tmB, W, 2, N, K, ldw, 128));
-  TAN_CHECK(make_tmap_2d(&tmOut, out_bf16, 2, M, N, ldo, 32));
+  tmOut = tmA;
+  if (out_bf16 != nullptr) TAN_CHECK(make_tmap_2d(&tmOut, out_bf16, 2, M, N, ldo, 32));
+  tmNA = tmOut;
+  tmNB = tmOut;
   ResLnArgs p;
   p.M = M;
   p.num_kb = K / kG2BK;
@@ -318,6 +385,31 @@ extern "C" int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W,
   p.beta = beta;
   p.x = x;
   p.ldx = ldx;
+  p.has_out = out_bf16 != nullptr;
+  p.emit = emit;
+  p.L = L > 0 ? L : M;
+  p.l_split = l_split > 0 ? l_split : p.L;
+  p.strideA = strideA;
+  p.strideB = strideB;
+  if (emit) {
+    // a warp stores 32 consecutive tokens as one box: they must share their clip and their part
+    if (M % p.L != 0 || p.L % 32 != 0 || p.l_split % 32 != 0 || p.l_split > p.L)
+      return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: stage emission needs M %% L == 0 and L, l_split %% 32 == 0");
+    if ((nrmA == nullptr) != (p.l_split == 0) && nrmA == nullptr)
+      return set_error(TAN_ERR_ARG, "tan_linear_res_ln: nrmA missing");
+    if (p.l_split < p.L && nrmB == nullptr) return set_error(TAN_ERR_ARG, "tan_linear_res_ln: nrmB missing");
+    const int64_t clips = M / p.L;
+    if (nrmA != nullptr) {
+      if ((reinterpret_cast<uintptr_t>(nrmA) & 15) || strideA < p.l_split)
+        return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: nrmA alignment / stride");
+      TAN_CHECK(make_tmap_2d(&tmNA, nrmA, 2, (clips - 1) * strideA + p.l_split, N, N, 32));
+    }
+    if (nrmB != nullptr && p.l_split < p.L) {
+      if ((reinterpret_cast<uintptr_t>(nrmB) & 15) || strideB < p.L - p.l_split)
+        return set_error(TAN_ERR_SHAPE, "tan_linear_res_ln: nrmB alignment / stride");
+      TAN_CHECK(make_tmap_2d(&tmNB, nrmB, 2, (clips - 1) * strideB + (p.L - p.l_split), N, N, 32));
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     TAN_CUDA(cudaFuncSetAttribute(gemm_res_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
@@ -326,5 +418,22 @@ extern "C" int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W,
   const int max_pairs = num_sms() / 2;
   const int pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
   return launch_pdl(gemm_res_ln_kernel, dim3(2 * pairs), dim3(kLnThreads), kLnSmem, static_cast<cudaStream_t>(stream), 2,
-                    tmA, tmB, tmOut, p);
+                    tmA, tmB, tmOut, tmNA, tmNB, p);
+}
+
+extern "C" int tan_linear_res_ln_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                      float* x, int64_t ldx, const float* gamma, const float* beta, void* out_bf16,
+                                      int64_t ldo, int M, int N, int K, void* stream) {
+  if (out_bf16 == nullptr) return set_error(TAN_ERR_ARG, "tan_linear_res_ln_bf16: null output");
+  return launch_res_ln(A, lda, W, ldw, bias, x, ldx, gamma, beta, out_bf16, ldo, M, N, K, 0, 0, nullptr, 0, nullptr, 0,
+                       stream);
+}
+
+extern "C" int tan_linear_res_ln_stage_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                            float* x, int64_t ldx, const float* gamma, const float* beta,
+                                            void* out_bf16, int64_t ldo, int M, int N, int K, int L, int l_split,
+                                            void* nrmA_bf16, int64_t strideA, void* nrmB_bf16, int64_t strideB,
+                                            void* stream) {
+  return launch_res_ln(A, lda, W, ldw, bias, x, ldx, gamma, beta, out_bf16, ldo, M, N, K, L, l_split, nrmA_bf16, strideA,
+                       nrmB_bf16, strideB, stream);
 }

@@ -148,6 +148,26 @@ def linear_res_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     _launches += 1
 
 
+def linear_res_ln_stage(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+                        gamma: torch.Tensor, beta: torch.Tensor, out_bf16: Optional[torch.Tensor], L: int,
+                        l_split: int, nrmA_bf16: Optional[torch.Tensor], strideA: int,
+                        nrmB_bf16: Optional[torch.Tensor], strideB: int) -> None:
+    """tan_linear_res_ln_stage_bf16: linear_res_ln + L2-normalised bf16 stage features scattered by clip
+    (nrm pointers are views whose data_ptr() is the stage's first row)."""
+    global _launches
+    M, K = a.shape
+    N = w.shape[0]
+    if _skip("linear", 2.0 * M * N * K):
+        return
+    with _timed("linear", 2.0 * M * N * K):
+        check(lib().tan_linear_res_ln_stage_bf16(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), x.data_ptr(), x.stride(0),
+            gamma.data_ptr(), beta.data_ptr(), _ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0,
+            M, N, K, L, l_split, _ptr(nrmA_bf16), strideA, _ptr(nrmB_bf16), strideB, _stream()),
+            "tan_linear_res_ln_stage_bf16")
+    _launches += 1
+
+
 def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=None, add_rows: int = 0,
               L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0,
               out_f32=None, out_bf16=None, l_split: int = 0, strideA: int = 0, strideB: int = 0,

@@ -57,7 +57,13 @@ class _Bf16Cache:
                 self.get(p)
 
 
-FUSE_OUTPROJ_LN = os.environ.get("TAN_FUSE_OUTPROJ_LN", "1") != "0"     # A/B aid
+# Fusion switches (A/B aids; defaults follow scripts/ab_fuse.py on B200):
+#   out-projection + residual + ln_2 (K = 512): 136 -> 111 us at 65 536 tokens, 33 -> 23 us at 16 384, neutral below
+#   c_proj + residual + next LayerNorm + stage features (K = 2048): 172 -> 193 us -- the wide tile gives up the
+#   overlap of MMAs and epilogue, which a K = 2048 GEMM needs -- so it stays off unless asked for.
+FUSE_OUTPROJ_LN = os.environ.get("TAN_FUSE_OUTPROJ_LN", "1") != "0"
+FUSE_OUTPROJ_LN_MIN_TOKENS = 12288
+FUSE_CPROJ_LN = os.environ.get("TAN_FUSE_CPROJ_LN", "0") != "0"
 
 
 def _f32(p: torch.Tensor) -> torch.Tensor:
@@ -129,14 +135,28 @@ def run_encoder_stack(blocks, x: torch.Tensor, kpm_u8: Optional[torch.Tensor], B
     S = len(blocks)
     M, d = x.shape
     sk = dict(l_split=sink.l_split, strideA=sink.strideA, strideB=sink.strideB)
+    l_split = min(sink.l_split, L) if sink.l_split > 0 else L
+
+    def fusable(emit: dict) -> bool:
+        """c_proj + residual + the following LayerNorm (+ bf16 stage features) in one kernel (tan_linear_res_ln_stage):
+        width 512, 32-token groups inside one clip and one part, and only the bf16 normalised features wanted."""
+        if not (FUSE_CPROJ_LN and d == 512 and L % 32 == 0 and l_split % 32 == 0):
+            return False
+        if not set(emit) <= {"nrmA_bf16", "nrmB_bf16"}:
+            return False
+        return (not emit) or ("nrmA_bf16" in emit and (l_split == L or "nrmB_bf16" in emit))
+
+    xn_ready = False          # buf.xn already holds ln_1 of the current block (written by the previous block's c_proj)
+    final_done = False
     for i, blk in enumerate(blocks):
-        emit = sink.stage_views(i - 1) if i >= 1 else {}
-        ops.layernorm(x, M, d, gamma=_f32(blk.ln_1.weight), beta=_f32(blk.ln_1.bias), L_in=L, out_bf16=buf.xn,
-                      **sk, **emit)
+        if not xn_ready:
+            emit = sink.stage_views(i - 1) if i >= 1 else {}
+            ops.layernorm(x, M, d, gamma=_f32(blk.ln_1.weight), beta=_f32(blk.ln_1.bias), L_in=L, out_bf16=buf.xn,
+                          **sk, **emit)
         ops.linear(buf.xn, cache.get(blk.attn.in_proj_weight), _f32(blk.attn.in_proj_bias), out_bf16=buf.qkv)
         ops.attention(buf.qkv[:, 0:d], buf.qkv[:, d:2 * d], buf.qkv[:, 2 * d:3 * d], kpm_u8, buf.att, B, blk.n_head,
                       L, L)
-        if d == 512 and FUSE_OUTPROJ_LN:
+        if d == 512 and FUSE_OUTPROJ_LN and M >= FUSE_OUTPROJ_LN_MIN_TOKENS:
             # out-projection + residual + ln_2 in one kernel: the fp32 residual stream is read and written once
             ops.linear_res_ln(buf.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), x,
                               _f32(blk.ln_2.weight), _f32(blk.ln_2.bias), buf.xn)
@@ -144,8 +164,21 @@ def run_encoder_stack(blocks, x: torch.Tensor, kpm_u8: Optional[torch.Tensor], B
             ops.linear(buf.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), residual=x, out_f32=x)
             ops.layernorm(x, M, d, gamma=_f32(blk.ln_2.weight), beta=_f32(blk.ln_2.bias), L_in=L, out_bf16=buf.xn)
         ops.linear(buf.xn, cache.get(blk.mlp.c_fc.weight), _f32(blk.mlp.c_fc.bias), out_bf16=buf.h, act=ACT_QUICKGELU)
-        ops.linear(buf.h, cache.get(blk.mlp.c_proj.weight), _f32(blk.mlp.c_proj.bias), residual=x, out_f32=x)
-    if emit_final and S >= 1:
+        # c_proj + residual, fused with the LayerNorm that consumes it: the next block's ln_1 (which also emits
+        # stage i) or the post-encoder LayerNorm (stage S-1)
+        last = i + 1 == S
+        nxt = blocks[i + 1].ln_1 if not last else (post_ln if emit_final else None)
+        emit = sink.stage_views(i) if (not last or emit_final) else {}
+        xn_ready = False
+        if nxt is not None and fusable(emit) and (not last or emit):
+            ops.linear_res_ln_stage(buf.h, cache.get(blk.mlp.c_proj.weight), _f32(blk.mlp.c_proj.bias), x,
+                                    _f32(nxt.weight), _f32(nxt.bias), None if last else buf.xn, L, l_split,
+                                    emit.get("nrmA_bf16"), sink.strideA, emit.get("nrmB_bf16"), sink.strideB)
+            xn_ready = not last
+            final_done = last
+        else:
+            ops.linear(buf.h, cache.get(blk.mlp.c_proj.weight), _f32(blk.mlp.c_proj.bias), residual=x, out_f32=x)
+    if emit_final and S >= 1 and not final_done:
         emit = sink.stage_views(S - 1)
         if post_ln is not None:
             ops.layernorm(x, M, d, gamma=_f32(post_ln.weight), beta=_f32(post_ln.bias), L_in=L, **sk, **emit)

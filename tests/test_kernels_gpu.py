@@ -111,6 +111,40 @@ def test_linear_res_ln(M, K):
     assert ((out.float() - y_ref).norm() / y_ref.norm()).item() < 4e-3
 
 
+@pytest.mark.parametrize("B,L,l_split,K,want_out", [(3, 288, 256, 2048, True), (5, 64, 64, 512, True), (2, 288, 256, 512, False)])
+def test_linear_res_ln_stage(B, L, l_split, K, want_out):
+    """c_proj + residual + LayerNorm + L2-normalised bf16 stage features scattered by clip (video | text parts)."""
+    ops = _ops()
+    M = B * L
+    g = torch.Generator().manual_seed(B * L + K)
+    a = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    w = (torch.randn(512, K, generator=g) * K ** -0.5).to(DEV).to(torch.bfloat16)
+    bias = torch.randn(512, generator=g).to(DEV)
+    x0 = (torch.randn(M, 512, generator=g) * 1.5 + 0.3).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(512, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(512, generator=g)).to(DEV)
+    x = x0.clone()
+    out = torch.full((M, 512), float("nan"), dtype=torch.bfloat16, device=DEV) if want_out else None
+    S, s_idx = 3, 1                                      # features land in stage 1 of a [B, S, T, d] / [S, B*N, d] pair
+    T, N = l_split, L - l_split
+    nrmA = torch.full((B, S, T, 512), float("nan"), dtype=torch.bfloat16, device=DEV)
+    nrmB = torch.full((S, B * N, 512), float("nan"), dtype=torch.bfloat16, device=DEV) if N > 0 else None
+    vA = nrmA.view(-1, 512)[s_idx * T:]
+    vB = nrmB.view(-1, 512)[s_idx * B * N:] if N > 0 else None
+    ops.linear_res_ln_stage(a, w, bias, x, gamma, beta, out, L, l_split, vA, S * T, vB, N)
+    x_ref = x0 + a.float() @ w.float().t() + bias
+    y_ref = torch.nn.functional.layer_norm(x_ref, (512,), gamma, beta, 1e-5)
+    n_ref = (y_ref / y_ref.norm(dim=-1, keepdim=True)).view(B, L, 512)
+    assert (x - x_ref).abs().max().item() < 2e-3
+    if want_out:
+        assert ((out.float() - y_ref).norm() / y_ref.norm()).item() < 4e-3
+    assert (nrmA[:, s_idx].float() - n_ref[:, :T]).abs().max().item() < 2e-3       # |values| <= 1, bf16
+    assert torch.isnan(nrmA[:, 0].float()).all() and torch.isnan(nrmA[:, 2].float()).all()   # other stages untouched
+    if N > 0:
+        assert (nrmB[s_idx].view(B, N, 512).float() - n_ref[:, T:]).abs().max().item() < 2e-3
+        assert torch.isnan(nrmB[0].float()).all() and torch.isnan(nrmB[2].float()).all()
+
+
 def test_linear_rejects_bad_shapes():
     from temporalalignnet_b200 import TanError
     ops = _ops()
