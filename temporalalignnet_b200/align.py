@@ -1,0 +1,112 @@
+"""Sliding-window text-to-video alignment of one long video: the 'overlap-seq' method of
+`eval/eval_zeroshot_align.py:125-205` -- overlapped temporal windows, per-window text subsets, stitch by
+averaging -- with ALL windows of the video batched into one forward of the dual and the joint stack.
+
+The reference runs every window as its own batch-1 call and, inside it, the joint model and the dual model
+as two more passes (`train/main.py:171-189`).  Here the windows become the clips of one batch: a short last
+window is padded with masked frames and every window's sentences are padded to the longest subset with masked
+sentences (masked keys never reach the softmax, so each window's result equals its stand-alone, unmasked
+computation); the per-window similarities are the own-clip blocks (tan_own_clip_sim) of the last stage.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import TanError
+from .tan_model import LazyLogits, TemporalAligner
+
+Window = Tuple[int, int, int, int]          # frames [t0, t1), sentences [n0, n1)
+
+
+def plan_windows(vlen: int, seq_len: int, text_mid_ts: Sequence[float], anchor_mask: Sequence[bool]) -> List[Window]:
+    """The window plan of eval/eval_zeroshot_align.py:128-171: windows of `seq_len` frames every seq_len/4
+    frames; a window's sentences are the index range spanned by the ANCHOR sentences (the reference uses the
+    non-alignable ones, whose ASR timestamps do not leak ground truth) whose mid timestamp lies within
+    [step - seq_len, step + 2*seq_len]; the first / last four windows extend to the first / last sentence."""
+    mid = np.asarray(text_mid_ts, dtype=np.float64)
+    anchors = np.arange(len(mid))[np.asarray(anchor_mask, dtype=bool)]
+    steps = np.arange(0, vlen - seq_len // 2, max(seq_len // 4, 1))
+    out: List[Window] = []
+    for idx, step in enumerate(steps):
+        act = anchors[(step - seq_len <= mid[anchors]) & (mid[anchors] <= step + 2 * seq_len)]
+        if len(act) == 0:
+            continue
+        left, right = int(act.min()), int(act.max())
+        if idx <= 3:
+            left = 0
+        elif idx >= len(steps) - 4:
+            right = len(mid) - 1
+        out.append((int(step), int(min(vlen, step + seq_len)), left, right + 1))
+    return out
+
+
+@torch.no_grad()
+def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_embed: torch.Tensor,
+                             windows: Sequence[Window], max_windows_per_batch: int = 256) -> dict:
+    """video [vlen, D_in] fp32 (CUDA), text_embed [n_text, D_text] fp32 (CUDA), windows from `plan_windows`.
+
+    Returns fp32 tensors: 'sim-joint' / 'sim-dual' [n_text, vlen] = last-stage logits / 0.07 averaged over the
+    windows that cover (sentence, frame) (eval_zeroshot_align.py:198-201), 'sim' = their mean (:205),
+    'overlap' [n_text, vlen] coverage counts, and, with an alignability head, 'alignability-dual' /
+    'alignability-joint' [n_text] (joint stage index 2, :184) averaged over windows (:203-204)."""
+    if not video.is_cuda:
+        raise TanError("sliding_window_alignment runs on a CUDA (sm_100a) device only; there is no CPU path")
+    if model.random_pos_start:
+        raise TanError("sliding_window_alignment needs random_pos_start=0 (deterministic positional offsets)")
+    dev = video.device
+    vlen, n_text = video.shape[0], text_embed.shape[0]
+    head = bool(model.use_alignability_head)
+    sim_j = torch.zeros(n_text, vlen, dtype=torch.float32, device=dev)
+    sim_d = torch.zeros_like(sim_j)
+    cover = torch.zeros_like(sim_j)
+    a_d = torch.zeros(n_text, dtype=torch.float32, device=dev)
+    a_j = torch.zeros_like(a_d)
+    a_n = torch.zeros_like(a_d)
+    windows = list(windows)
+    for w0 in range(0, len(windows), max_windows_per_batch):
+        chunk = windows[w0:w0 + max_windows_per_batch]
+        W = len(chunk)
+        T = max(t1 - t0 for t0, t1, _, _ in chunk)
+        N = max(n1 - n0 for _, _, n0, n1 in chunk)
+        vb = torch.zeros(W, T, video.shape[1], dtype=torch.float32, device=dev)
+        tb = torch.zeros(W, N, text_embed.shape[1], dtype=torch.float32, device=dev)
+        vpm = torch.ones(W, T, dtype=torch.bool, device=dev)
+        tpm = torch.ones(W, N, dtype=torch.bool, device=dev)
+        for i, (t0, t1, n0, n1) in enumerate(chunk):
+            vb[i, :t1 - t0] = video[t0:t1]
+            tb[i, :n1 - n0] = text_embed[n0:n1]
+            vpm[i, :t1 - t0] = False
+            tpm[i, :n1 - n0] = False
+        out = model._forward_impl(vb, tb, vpm, tpm)
+        blocks = {}
+        for key in ("logits_dual", "logits_joint"):
+            lg: LazyLogits = out[key]
+            Bv, S, Tv, d = lg.vfeat.shape
+            blocks[key] = ops.own_clip_sim(lg.vfeat, lg.tfeat, lg.shared_text, Bv, S, Tv, N, d, s_first=S - 1,
+                                           s_count=1)[:, 0] / 0.07                     # [W, T, N]
+        for i, (t0, t1, n0, n1) in enumerate(chunk):
+            sim_j[n0:n1, t0:t1] += blocks["logits_joint"][i, :t1 - t0, :n1 - n0].t()
+            sim_d[n0:n1, t0:t1] += blocks["logits_dual"][i, :t1 - t0, :n1 - n0].t()
+            cover[n0:n1, t0:t1] += 1
+            if head:
+                a_d[n0:n1] += out["dual_logits_alignability"][i, :n1 - n0, 0]
+                a_j[n0:n1] += out["joint_logits_alignability"][i, 2, :n1 - n0, 0]
+                a_n[n0:n1] += 1
+    eps = 1e-5
+    res = {"sim-joint": sim_j / cover.clamp(min=eps), "sim-dual": sim_d / cover.clamp(min=eps), "overlap": cover}
+    res["sim"] = (res["sim-joint"] + res["sim-dual"]) / 2
+    if head:
+        res["alignability-dual"] = a_d / a_n.clamp(min=eps)
+        res["alignability-joint"] = a_j / a_n.clamp(min=eps)
+    return res
+
+
+def predicted_frames(sim: torch.Tensor) -> torch.Tensor:
+    """Per sentence, the frame the alignment picks (eval_zeroshot_align.py:222-238: uncovered entries count as
+    -6e4, softmax over time, argmax)."""
+    s = sim.masked_fill(sim == 0, -6e4)
+    return s.softmax(-1).argmax(-1)
