@@ -260,8 +260,9 @@ def run_gpu_arm(args):
         lin = agg["linear"]
         lin_tf = lin[0] / (lin[1] * 1e-3) / 1e12
         kernel_ms = {k: round(v[1] / steps, 4) for k, v in agg.items()}
-        roofline = {"kernel": "umma_gemm2_kernel<LinearEpi2> (tan_linear_bf16: QKV/out/MLP/pre projections; the "
-                              "kernel class with the largest share of the step)",
+        roofline = {"kernel": "umma_gemm2_kernel<LinearEpi2> + gemm_res_ln_kernel (tan_linear_bf16 / tan_linear_res_ln_bf16: "
+                              "pre / QKV / MLP projections, out-projection fused with residual + ln_2; the kernel class "
+                              "with the largest share of the step)",
                     "bound": "tensor", "achieved": round(lin_tf, 1), "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": round(lin_tf / tf_peak, 4),
                     "traffic": (traffic.get("linear") or {}).get("bytes_per_launch") if world == 1 else None,

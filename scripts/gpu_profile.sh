@@ -14,7 +14,7 @@ echo "== ncu launch list (3rd eager step, one stream so that the order is the pr
 timeout 900 $NCU --metrics gpu__time_duration.sum -s 230 -c 130 --csv --log-file gpurun_out/${TAG}_launches.csv \
    python scripts/prof_step.py 256 3 --one-stream > gpurun_out/${TAG}_list.log 2>&1; echo rc=$?; tail -2 gpurun_out/${TAG}_list.log
 echo "== ncu full: linear GEMMs (pre-projections + first layer)"
-timeout 900 $NCU --kernel-name-base demangled --set full --import-source on -k regex:LinearEpi2 -s 100 -c 7 -o gpurun_out/${TAG}_prof_gemm \
+timeout 900 $NCU --kernel-name-base demangled --set full --import-source on -k regex:"LinearEpi2|gemm_res_ln" -s 100 -c 7 -o gpurun_out/${TAG}_prof_gemm \
    python scripts/prof_step.py 256 3 --one-stream > gpurun_out/${TAG}_ncu_gemm.log 2>&1; echo rc=$?
 echo "== ncu full: fused sim+NCE"
 timeout 900 $NCU --set full --import-source on -k regex:"sim_fused_kernel|sim_reduce_partials" -s 8 -c 4 -o gpurun_out/${TAG}_prof_sim \

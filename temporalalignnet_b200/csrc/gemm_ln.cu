@@ -163,8 +163,10 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const float4* evec = reinterpret_cast<const float4*>(vecs + 2 * kLnN + half * 256);
     uint32_t acc_phase = 0;
     const int rr = lane >> 3, cc = lane & 7;
-    // The residual rows of a tile are pulled into L2 one whole tile ahead (this epilogue does not overlap the
-    // MMAs, so an HBM round trip per 32-feature chunk would be fully exposed): lane = row, 8 lines of 128 bytes.
+    // The residual rows of a tile are pulled into L2 while its MMAs run (the epilogue warps idle then; this
+    // epilogue does not overlap the MMAs, so an HBM round trip per 32-feature chunk would be fully exposed;
+    // prefetching a whole tile earlier was measured to be evicted again: 38 % L2 hits, ncu r01f): lane = row,
+    // 8 lines of 128 bytes.
     auto prefetch_residual = [&](int t) {
       const int row = t * 2 * kG2BM + static_cast<int>(rank) * kG2BM + quarter * 32 + lane;
       if (t < p.n_tiles && row < p.M) {
@@ -173,9 +175,8 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + i * 128));
       }
     };
-    prefetch_residual(pair_id);
     for (int t = pair_id; t < p.n_tiles; t += num_pairs) {
-      prefetch_residual(t + num_pairs);
+      prefetch_residual(t);
       const int row0 = t * 2 * kG2BM + static_cast<int>(rank) * kG2BM + quarter * 32;
       const int col0 = half * 256;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + col0;
