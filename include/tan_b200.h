@@ -271,6 +271,72 @@ TAN_API int tan_agree_targets(const uint32_t* old_posbits, const int* win_joint,
                       const uint8_t* replace, int B, int T, int N, int kind, uint32_t* new_posbits,
                       void* stream);
 
+/* ---- backward pass (training step) ----------------------------------------------------------------
+ * train/main.py:112 calls loss.backward(); in the reference every gradient is produced by torch autograd over the
+ * call sites cited above.  Here the GEMM-shaped gradients (dgrad = dY @ W, wgrad = dY^T @ X, the similarity
+ * recomputation and its two gradient products) are tan_linear_bf16 calls on transposed operands; the entry
+ * points below are the rest.  Round-1 status: first correct path. */
+
+/* out[c, r] = in[r, c] (bf16) for r < R; columns R <= r < R_pad of out are written as zero (contraction padding to
+ * the GEMM's K % 64).  in [R, C] (ldi), out [C, R_pad] (ldo); C, R_pad, ldi, ldo even. */
+TAN_API int tan_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int R_pad,
+                               void* stream);
+
+/* out[n] (+)= sum_m in[m, n]: bias gradients (autograd of the `+ bias` in F.linear).  in [M, N] bf16 or fp32 (ld),
+ * out [N] fp32; deterministic two-stage reduction through `workspace`. */
+TAN_API size_t tan_colsum_workspace_bytes(int M, int N);
+TAN_API int tan_colsum(const void* in, int in_is_bf16, int64_t ld, int M, int N, float* out, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* QuickGELU on a stored pre-activation and its derivative (model/tfm_model.py:11-13): h = u * sigmoid(1.702 u);
+ * du = dh * s (1 + 1.702 u (1 - s)), s = sigmoid(1.702 u).  bf16 [n], n % 8 == 0, 16-byte aligned. */
+TAN_API int tan_quickgelu_fwd(const void* u, void* h, size_t n, void* stream);
+TAN_API int tan_quickgelu_bwd(const void* dh, const void* u, void* du, size_t n, void* stream);
+
+/* Backward of tan_layernorm's y = LayerNorm(x) * gamma + beta with the same row map (row r of x <-> row
+ * (r / L_in) * L_out + l_off + r % L_in of dy):  dx[r] (+)= the LayerNorm input gradient (accumulate_dx != 0 adds
+ * to dx: the residual stream's gradient), dgamma / dbeta [d] are ACCUMULATED (NULL: skipped).  x, dx [rows, d]
+ * fp32, dy fp32.  Replaces autograd of nn.LayerNorm at model/tfm_model.py:31,:37, model/tan_model.py:155,:161-167,
+ * :174,:187,:206,:233. */
+TAN_API size_t tan_layernorm_bwd_workspace_bytes(int rows, int d);
+TAN_API int tan_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate_dx,
+                              int rows, int d, int L_in, int L_out, int l_off, float* dgamma, float* dbeta,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137): dst = (g - y <y, g>) / ||x||.  x and g share the
+ * stage-feature layout (row r at (r / L_in) * src_stride + r % L_in), dst is token-major (row
+ * (r / L_in) * L_out + l_off + r % L_in); written, or added when accumulate != 0.  fp32. */
+TAN_API int tan_l2norm_bwd(const float* x, const float* g, float* dst, int accumulate, int rows, int d, int L_in,
+                           int64_t src_stride, int L_out, int l_off, void* stream);
+
+/* out[l, :] (+)= sum_b in[b * L_out + l_off + l, :]: gradient of a positional table broadcast over the clips
+ * (model/tan_model.py:161-167).  fp32. */
+TAN_API int tan_batch_sum(const float* in, float* out, int B, int L, int d, int L_out, int l_off, int accumulate,
+                          void* stream);
+
+/* Gradient of the MIL-NCE loss with respect to a block of cosines (train/loss.py:231-275 differentiated).
+ * z [Rc, ldz] fp32: cosines of rows r0 .. r0+Rc of ONE stage (row = b * T + t, local clips) against all C global
+ * columns (g->C; g->S is ignored).  With e = exp((z - 1) / 0.07) on valid columns,
+ *   G[r, c] = e (ra[r] + cb[c] - positive(r, c) (rap[r] + cbp[c])) / 0.07
+ * ra / rap [B_loc * T]: weight / sum_all and weight / sum_pos of the row (0 when the row does not count),
+ * cb / cbp [C] the same for the stage's columns.  Writes G [Rc, ldg] bf16 (columns up to ldg zero-filled) and
+ * GT [C, ldgt] bf16 = G^T with columns Rc .. Rc_pad zero-filled: the operands of dA = G @ tfeat and
+ * dB = G^T @ vfeat. */
+TAN_API int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pad, int r0, const tan_sim_geom* g,
+                               const uint32_t* posbits, const uint8_t* col_valid, const uint8_t* row_kill,
+                               const float* ra, const float* rap, const float* cb, const float* cbp, void* G,
+                               int64_t ldg, void* GT, int64_t ldgt, void* stream);
+
+/* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
+ * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
+ * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from
+ * model/tfm_model.py:32. */
+TAN_API int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                   const void* o, int64_t ldo, const void* d_out, int64_t lddo,
+                                   const uint8_t* key_padding_mask, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                                   void* dv, int64_t lddv, float* lse, float* delta, int B, int H, int Lq, int Lk,
+                                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ TAN_OK = 0
 ERR_NAMES = {-1: "TAN_ERR_SHAPE", -2: "TAN_ERR_ARCH", -3: "TAN_ERR_WORKSPACE", -4: "TAN_ERR_CUDA",
              -5: "TAN_ERR_ARG"}
 ACT_NONE, ACT_QUICKGELU = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TanError(RuntimeError):
@@ -83,6 +83,29 @@ SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tan_agree_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_void_p, C.c_void_p]),
+    # ---- backward pass -------------------------------------------------------------------------------
+    "tan_transpose_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p]),
+    "tan_colsum_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "tan_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                             C.c_size_t, C.c_void_p]),
+    "tan_quickgelu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tan_quickgelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tan_layernorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "tan_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+    "tan_l2norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                 C.c_int, C.c_int, C.c_void_p]),
+    "tan_batch_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "tan_sim_grad_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(SimGeom), C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tan_attention_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,899 @@
+// Backward-pass kernels of the TAN hot path (training step): everything that is NOT a plain GEMM.
+// The GEMM-shaped part of the backward pass (dgrad = dY @ W, wgrad = dY^T @ X, the similarity-matrix
+// recomputation and its two gradient products) runs on the tcgen05 pair GEMM of gemm_linear.cu through
+// tan_linear_bf16 with transposed operands; this file provides the operand transposes, the bias / LayerNorm
+// parameter reductions, QuickGELU, LayerNorm, L2-normalisation, the similarity-gradient tile kernel and the
+// attention backward kernels.
+//
+// Status (round 1): first correct path.  The attention backward uses the legacy warp-level tensor path
+// (mma.sync through nvcuda::wmma) and recomputes the score tiles in two kernels (dQ + softmax statistics,
+// then dK / dV) so that no atomics are needed and the result is deterministic; a tcgen05 version with the
+// accumulators in TMEM is the follow-up.
+#include <mma.h>
+
+#include "common.cuh"
+
+namespace tanb {
+
+// ------------------------------------------------------------------------------------------------
+// bf16 transpose with zero padding of the contraction tail: out[c, r] = in[r, c] for r < R, 0 for R <= r < Rp.
+// 64 x 64 tiles through shared memory, 32-bit global accesses on both sides.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ in, int64_t ldi,
+                                                             bf16* __restrict__ out, int64_t ldo, int R, int C,
+                                                             int Rp) {
+  __shared__ uint16_t tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(in);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+    uint32_t v = 0;
+    if (r < R && c < C) v = *reinterpret_cast<const uint32_t*>(src + static_cast<int64_t>(r) * ldi + c);   // C is even
+    tile[ty + 8 * i][2 * tx] = static_cast<uint16_t>(v & 0xffffu);
+    tile[ty + 8 * i][2 * tx + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  __syncthreads();
+  uint16_t* dst = reinterpret_cast<uint16_t*>(out);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + 2 * tx;
+    if (c < C && r < Rp) {                                     // Rp is even
+      const uint32_t v = static_cast<uint32_t>(tile[2 * tx][ty + 8 * i]) |
+                         (static_cast<uint32_t>(tile[2 * tx + 1][ty + 8 * i]) << 16);
+      *reinterpret_cast<uint32_t*>(dst + static_cast<int64_t>(c) * ldo + r) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums (bias gradients): partial[p, n] = sum over the rows of slab p of in[m, n]; finished by
+// colsum_finish_kernel in a fixed order (deterministic, no atomics).
+// ------------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const void* __restrict__ in, int64_t ld, int M, int N,
+                                                             int rows_per_slab, float* __restrict__ partial) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + 2 * tx;
+  const int m0 = blockIdx.y * rows_per_slab;
+  const int m1 = min(m0 + rows_per_slab, M);
+  float s0 = 0.f, s1 = 0.f;
+  if (n < N) {
+    for (int m = m0 + ty; m < m1; m += 8) {
+      if (BF16) {
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(static_cast<const bf16*>(in) + static_cast<int64_t>(m) * ld + n);
+        const float2 f = unpack_bf16x2(u);
+        s0 += f.x; s1 += f.y;
+      } else {
+        const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(in) + static_cast<int64_t>(m) * ld + n);
+        s0 += f.x; s1 += f.y;
+      }
+    }
+  }
+  red[ty][2 * tx] = s0;
+  red[ty][2 * tx + 1] = s1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int nn = blockIdx.x * 64 + threadIdx.x;
+    if (nn < N) partial[static_cast<int64_t>(blockIdx.y) * N + nn] = s;
+  }
+}
+
+// out[n] = (accumulate ? out[n] : 0) + sum_p partial[p, n]
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int P, int N, float* __restrict__ out,
+                                     int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += partial[static_cast<int64_t>(p) * N + n];
+  out[n] = accumulate ? out[n] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QuickGELU (model/tfm_model.py:11-13) forward on the stored pre-activation and its backward.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256) quickgelu_fwd_kernel(const uint4* __restrict__ u, uint4* __restrict__ h, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = u[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      o[j] = pack_bf16x2(f.x * sigmoid_f(1.702f * f.x), f.y * sigmoid_f(1.702f * f.y));
+    }
+    h[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__device__ __forceinline__ float quickgelu_grad(float x) {
+  const float s = sigmoid_f(1.702f * x);
+  return s * (1.0f + 1.702f * x * (1.0f - s));
+}
+
+__global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ u,
+                                                            uint4* __restrict__ du, size_t n8) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 a = dh[i], b = u[i];
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 g = unpack_bf16x2(wa[j]), x = unpack_bf16x2(wb[j]);
+      o[j] = pack_bf16x2(g.x * quickgelu_grad(x.x), g.y * quickgelu_grad(x.y));
+    }
+    du[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  Forward: y = (x - mean) * rstd * gamma + beta, row r of x -> row map(r) of y with
+// map(r) = (r / L_in) * L_out + l_off + r % L_in (the concat scatter of tan_layernorm).
+//   dx[r] (+)= rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy[map(r)] * gamma
+//   partial dgamma / dbeta per block, finished in a fixed order by ln_param_finish_kernel.
+// Warp per row, the row lives in registers (statistics are recomputed from x, as in the forward kernel).
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ gamma, float* __restrict__ dx,
+                                                            int accumulate, int rows, int d, int L_in, int L_out,
+                                                            int l_off, float* __restrict__ partial) {
+  __shared__ float red[8][V * 128];
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float dg[V * 4], db[V * 4];
+#pragma unroll
+  for (int i = 0; i < V * 4; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+  float gm[V * 4];
+  if (gamma != nullptr) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      gm[4 * i] = g.x; gm[4 * i + 1] = g.y; gm[4 * i + 2] = g.z; gm[4 * i + 3] = g.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) gm[i] = 1.f;
+  }
+  for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
+    const int b = r / L_in, l = r - b * L_in;
+    const int64_t yr = static_cast<int64_t>(b) * L_out + l_off + l;
+    float xv[V * 4], gv[V * 4];
+    const float4* px = reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * d);
+    const float4* py = reinterpret_cast<const float4*>(dy + yr * d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 a = px[i * 32 + lane], g = py[i * 32 + lane];
+      xv[4 * i] = a.x; xv[4 * i + 1] = a.y; xv[4 * i + 2] = a.z; xv[4 * i + 3] = a.w;
+      gv[4 * i] = g.x; gv[4 * i + 1] = g.y; gv[4 * i + 2] = g.z; gv[4 * i + 3] = g.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) s += xv[i];
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
+    const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) {
+      xv[i] *= rstd;                       // xhat
+      dg[i] += gv[i] * xv[i];
+      db[i] += gv[i];
+      gv[i] *= gm[i];                      // g
+      sg += gv[i];
+      sgx += gv[i] * xv[i];
+    }
+    const float mg = warp_sum(sg) / d, mgx = warp_sum(sgx) / d;
+    float4* pd = reinterpret_cast<float4*>(dx + static_cast<int64_t>(r) * d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = rstd * (gv[4 * i] - mg - xv[4 * i] * mgx);
+      o.y = rstd * (gv[4 * i + 1] - mg - xv[4 * i + 1] * mgx);
+      o.z = rstd * (gv[4 * i + 2] - mg - xv[4 * i + 2] * mgx);
+      o.w = rstd * (gv[4 * i + 3] - mg - xv[4 * i + 3] * mgx);
+      if (accumulate) {
+        const float4 p = pd[i * 32 + lane];
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      pd[i * 32 + lane] = o;
+    }
+  }
+  if (partial == nullptr) return;
+  // block reduction of dgamma then dbeta over the 8 warps (column j of lane: 128 i + 4 lane + k)
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) red[warp][i * 128 + 4 * lane + k] = pass == 0 ? dg[4 * i + k] : db[4 * i + k];
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < warps_per_block; ++w) t += red[w][j];
+      partial[(static_cast<int64_t>(blockIdx.x) * 2 + pass) * d + j] = t;
+    }
+  }
+}
+
+// dgamma[j] += sum_p partial[p][0][j], dbeta[j] += sum_p partial[p][1][j]  (accumulated: one LayerNorm may serve
+// several calls of a step, e.g. ln_video_init in the video and the joint stack)
+__global__ void ln_param_finish_kernel(const float* __restrict__ partial, int blocks, int d, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  float g = 0.f, b = 0.f;
+  for (int p = 0; p < blocks; ++p) {
+    g += partial[(static_cast<int64_t>(p) * 2) * d + j];
+    b += partial[(static_cast<int64_t>(p) * 2 + 1) * d + j];
+  }
+  dgamma[j] += g;
+  dbeta[j] += b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137) with row maps on both sides:
+//   src row (raw features x and incoming gradient g):  (r / L_in) * src_stride + r % L_in
+//   dst row (token-major gradient buffer):            (r / L_in) * L_out + l_off + r % L_in
+//   dst = (g - y * <y, g>) / ||x||        (written, or added when accumulate != 0)
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                         float* __restrict__ dst, int accumulate, int rows, int d,
+                                                         int L_in, int64_t src_stride, int L_out, int l_off) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const int b = r / L_in, l = r - b * L_in;
+    const int64_t sr = static_cast<int64_t>(b) * src_stride + l;
+    const int64_t dr = static_cast<int64_t>(b) * L_out + l_off + l;
+    float xv[V * 4], gv[V * 4];
+    const float4* px = reinterpret_cast<const float4*>(x + sr * d);
+    const float4* pg = reinterpret_cast<const float4*>(g + sr * d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 a = px[i * 32 + lane], c = pg[i * 32 + lane];
+      xv[4 * i] = a.x; xv[4 * i + 1] = a.y; xv[4 * i + 2] = a.z; xv[4 * i + 3] = a.w;
+      gv[4 * i] = c.x; gv[4 * i + 1] = c.y; gv[4 * i + 2] = c.z; gv[4 * i + 3] = c.w;
+    }
+    float q = 0.f, xg = 0.f;
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) { q += xv[i] * xv[i]; xg += xv[i] * gv[i]; }
+    q = warp_sum(q);
+    xg = warp_sum(xg);
+    const float inv = 1.0f / sqrtf(q);
+    const float k = xg / q;                    // <y, g> / ||x|| * (1 / ||x||) applied to x:  y <y,g> = x * xg / q
+    float4* pd = reinterpret_cast<float4*>(dst + dr * d);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = (gv[4 * i] - xv[4 * i] * k) * inv;
+      o.y = (gv[4 * i + 1] - xv[4 * i + 1] * k) * inv;
+      o.z = (gv[4 * i + 2] - xv[4 * i + 2] * k) * inv;
+      o.w = (gv[4 * i + 3] - xv[4 * i + 3] * k) * inv;
+      if (accumulate) {
+        const float4 p = pd[i * 32 + lane];
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      pd[i * 32 + lane] = o;
+    }
+  }
+}
+
+// out[l, :] (+)= sum_b in[(b * L_out + l_off + l), :]   (gradient of a table broadcast over the batch)
+__global__ void __launch_bounds__(256) batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                        int L, int d, int L_out, int l_off, int accumulate) {
+  const int64_t n = static_cast<int64_t>(L) * d;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>(i / d), j = static_cast<int>(i - static_cast<int64_t>(l) * d);
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += in[(static_cast<int64_t>(b) * L_out + l_off + l) * d + j];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Similarity-gradient tiles.  z [Rc, ldz] fp32 cosines of rows (b, t) = r0 + row of ONE stage against all
+// columns; with e = exp((z - 1) / 0.07) on valid columns (the forward's fixed shift):
+//   G[r, c] = e * (ra[r] + cb[c] - pos(r, c) * (rap[r] + cbp[c])) / 0.07      = d loss / d cos[r, c]
+// ra / rap = w_row / sum_all, w_row / sum_pos of the row (0 for rows that do not count), cb / cbp the same for
+// columns of this stage (train/loss.py:248-256 differentiated; see loss.py for the weights).
+// Writes G [Rc, ldg] bf16 and its transpose GT [C, ldgt] bf16 (zero for Rc <= r < Rcp) -- the operands of the
+// two gradient GEMMs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sim_grad_kernel(const float* __restrict__ z, int64_t ldz, int Rc, int Rcp, int C,
+                                                       int Cp, int r0, int T, int N, int W, int b_off,
+                                                       const uint32_t* __restrict__ posbits,
+                                                       const uint8_t* __restrict__ col_valid,
+                                                       const uint8_t* __restrict__ row_kill,
+                                                       const float* __restrict__ ra, const float* __restrict__ rap,
+                                                       const float* __restrict__ cb, const float* __restrict__ cbp,
+                                                       bf16* __restrict__ G, int64_t ldg, bf16* __restrict__ GT,
+                                                       int64_t ldgt) {
+  __shared__ uint16_t tile[64][66];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int rt = blockIdx.x * 64, ct = blockIdx.y * 64;
+  constexpr float kInvTau = 1.0f / 0.07f;
+  constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = rt + ty + 8 * i;              // row inside the chunk
+    const int c = ct + 2 * tx;
+    float g0 = 0.f, g1 = 0.f;
+    if (rl < Rc && c < C) {
+      const int r = r0 + rl;                     // row of the stage: (b, t)
+      const int b = r / T, t = r - b * T;
+      const float2 zz = *reinterpret_cast<const float2*>(z + static_cast<int64_t>(rl) * ldz + c);
+      const float a = ra[r], ap = rap[r];
+      const bool kill = row_kill != nullptr && row_kill[r] != 0;
+      const int own0 = (b_off + b) * N;
+      const float zv[2] = {zz.x, zz.y};
+      float gv[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int cc = c + k;
+        float gg = 0.f;
+        if (cc < C && col_valid[cc] != 0) {
+          const int n = cc - own0;
+          const bool own = n >= 0 && n < N;
+          if (!(own && kill)) {
+            const float e = exp2f((zv[k] - 1.0f) * (kInvTau * kLog2e));
+            float coef = a + cb[cc];
+            if (own && ((posbits[(static_cast<int64_t>(b) * T + t) * W + (n >> 5)] >> (n & 31)) & 1u))
+              coef -= ap + cbp[cc];
+            gg = e * coef * kInvTau;
+          }
+        }
+        gv[k] = gg;
+      }
+      g0 = gv[0]; g1 = gv[1];
+    }
+    const uint32_t packed = pack_bf16x2(g0, g1);
+    tile[ty + 8 * i][2 * tx] = static_cast<uint16_t>(packed & 0xffffu);
+    tile[ty + 8 * i][2 * tx + 1] = static_cast<uint16_t>(packed >> 16);
+    if (rl < Rc && c < Cp) *reinterpret_cast<uint32_t*>(G + static_cast<int64_t>(rl) * ldg + c) = packed;
+  }
+  __syncthreads();
+  uint16_t* dst = reinterpret_cast<uint16_t*>(GT);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = ct + ty + 8 * i, rl = rt + 2 * tx;
+    if (c < C && rl < Rcp) {
+      const uint32_t v = static_cast<uint32_t>(tile[2 * tx][ty + 8 * i]) |
+                         (static_cast<uint32_t>(tile[2 * tx + 1][ty + 8 * i]) << 16);
+      *reinterpret_cast<uint32_t*>(dst + static_cast<int64_t>(c) * ldgt + rl) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention backward (head_dim 64), per (clip b, head h).  With s_ij = q_i . k_j / 8 + mask_j,
+// p_ij = softmax_j s_ij, o_i = sum_j p_ij v_j and the incoming gradient do_i:
+//   delta_i = <do_i, o_i>,  dp_ij = <do_i, v_j>,  ds_ij = p_ij (dp_ij - delta_i)
+//   dq_i = sum_j ds_ij k_j / 8,   dk_j = sum_i ds_ij q_i / 8,   dv_j = sum_i p_ij do_i.
+// Kernel A (CTA = 64 queries): pass 1 recomputes the scores to get lse_i, pass 2 accumulates dq; writes lse and
+// delta.  Kernel B (CTA = 64 keys): walks the query blocks and accumulates dk, dv.  bf16 operands, fp32
+// accumulation (wmma m16n16k16), 4 warps: warp w owns 16 of the CTA's 64 rows.
+// ------------------------------------------------------------------------------------------------
+namespace wm = nvcuda::wmma;
+constexpr int kAB = 64;          // block edge (queries / keys per CTA step)
+constexpr int kAP = 72;          // bf16 smem row pitch (elements)
+constexpr int kAF = 68;          // fp32 smem row pitch (elements)
+constexpr float kAttScale = 0.125f;
+
+struct AttnBwdSmem {
+  bf16 q[kAB][kAP];
+  bf16 dO[kAB][kAP];
+  bf16 k[kAB][kAP];
+  bf16 v[kAB][kAP];
+  bf16 p[kAB][kAP];
+  bf16 ds[kAB][kAP];
+  float s[kAB][kAF];
+  float dp[kAB][kAF];
+  float lse[kAB];
+  float delta[kAB];
+  float bias[kAB];       // 0 or -inf per key of the current block
+};
+
+// rows [row0, row0 + 64) x 64 columns of a [*, ld] bf16 matrix (columns col0..col0+63) -> smem, zero beyond n_rows
+__device__ __forceinline__ void attn_load_block(bf16 (*dst)[kAP], const bf16* src, int64_t ld, int row0, int n_rows,
+                                                int64_t base_row, int col0) {
+  for (int i = threadIdx.x; i < kAB * 8; i += blockDim.x) {
+    const int r = i >> 3, c8 = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row0 + r < n_rows) v = *reinterpret_cast<const uint4*>(src + (base_row + row0 + r) * ld + col0 + c8);
+    *reinterpret_cast<uint4*>(&dst[r][c8]) = v;
+  }
+}
+
+// acc[16 x 64] (4 n-tiles) (+)= A_w[16 x 64] (row-major in smem) @ B^T where B is [64 n][64 k] row-major (i.e. col_major B)
+__device__ __forceinline__ void mm_a_bt(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], const bf16* a_rows,
+                                        const bf16 (*bmat)[kAP]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::row_major> fa;
+    wm::load_matrix_sync(fa, a_rows + kk * 16, kAP);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::col_major> fb;
+      wm::load_matrix_sync(fb, &bmat[j * 16][kk * 16], kAP);
+      wm::mma_sync(acc[j], fa, fb, acc[j]);
+    }
+  }
+}
+
+// acc[16 x 64] += A_w[16 x 64] (row-major) @ B where B is [64 k][64 n] row-major
+__device__ __forceinline__ void mm_a_b(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], const bf16* a_rows,
+                                       const bf16 (*bmat)[kAP]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::row_major> fa;
+    wm::load_matrix_sync(fa, a_rows + kk * 16, kAP);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::row_major> fb;
+      wm::load_matrix_sync(fb, &bmat[kk * 16][j * 16], kAP);
+      wm::mma_sync(acc[j], fa, fb, acc[j]);
+    }
+  }
+}
+
+// acc[16 x 64] += A^T_w @ B: A is [64 k][64 m] row-major in smem, this warp takes columns m0..m0+15 of it
+__device__ __forceinline__ void mm_at_b(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4],
+                                        const bf16 (*amat)[kAP], int m0, const bf16 (*bmat)[kAP]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::col_major> fa;
+    wm::load_matrix_sync(fa, &amat[kk * 16][m0], kAP);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::row_major> fb;
+      wm::load_matrix_sync(fb, &bmat[kk * 16][j * 16], kAP);
+      wm::mma_sync(acc[j], fa, fb, acc[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void acc_zero(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wm::fill_fragment(acc[j], 0.f);
+}
+
+__device__ __forceinline__ void acc_store(const wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], float* rows) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) wm::store_matrix_sync(rows + j * 16, acc[j], kAF, wm::mem_row_major);
+}
+
+struct AttnBwdArgs {
+  const bf16* q; int64_t ldq;
+  const bf16* k; int64_t ldk;
+  const bf16* v; int64_t ldv;
+  const bf16* o; int64_t ldo;
+  const bf16* dO; int64_t lddo;
+  const uint8_t* kpm;
+  bf16* dq; int64_t lddq;
+  bf16* dk; int64_t lddk;
+  bf16* dv; int64_t lddv;
+  float* lse;      // [B, H, Lq]
+  float* delta;    // [B, H, Lq]
+  int B, H, Lq, Lk;
+};
+
+__device__ __forceinline__ void attn_fill_bias(float* bias, const uint8_t* kpm, int b, int Lk, int k0) {
+  for (int j = threadIdx.x; j < kAB; j += blockDim.x) {
+    const int key = k0 + j;
+    bias[j] = (key < Lk && (kpm == nullptr || kpm[static_cast<int64_t>(b) * Lk + key] == 0)) ? 0.f : -INFINITY;
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_raw);
+  const int q0 = blockIdx.x * kAB, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp * 16 + (lane >> 1);           // this lane's query row inside the block
+  const int cbeg = (lane & 1) * 32;                   // and its 32 key columns
+  const int64_t qbase = static_cast<int64_t>(b) * a.Lq, kbase = static_cast<int64_t>(b) * a.Lk;
+
+  attn_load_block(sm.q, a.q, a.ldq, q0, a.Lq, qbase, h * 64);
+  attn_load_block(sm.dO, a.dO, a.lddo, q0, a.Lq, qbase, h * 64);
+  // delta_i = <do_i, o_i>: two lanes per row, 32 features each
+  float delta = 0.f;
+  if (q0 + row < a.Lq) {
+    const bf16* po = a.o + (qbase + q0 + row) * a.ldo + h * 64 + cbeg;
+    const bf16* pd = a.dO + (qbase + q0 + row) * a.lddo + h * 64 + cbeg;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(po + j));
+      const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pd + j));
+      delta += x.x * y.x + x.y * y.y;
+    }
+  }
+  delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+
+  // ---- pass 1: lse_i -------------------------------------------------------------------------
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < a.Lk; k0 += kAB) {
+    __syncthreads();
+    attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
+    attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
+    __syncthreads();
+    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
+    acc_zero(acc);
+    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);
+    acc_store(acc, &sm.s[warp * 16][0]);
+    __syncwarp();
+    float bm = -INFINITY;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) bm = fmaxf(bm, sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j]);
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+    const float mn = fmaxf(m, bm);
+    const float ref = mn == -INFINITY ? 0.f : mn;      // all keys so far masked: every term below is exp(-inf) = 0
+    float ps = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) ps += __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - ref);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+    l = l * __expf(m - ref) + ps;
+    m = mn;
+    __syncwarp();
+  }
+  const float lse = m + __logf(l);
+  if ((lane & 1) == 0 && q0 + row < a.Lq) {
+    const int64_t idx = (static_cast<int64_t>(b) * a.H + h) * a.Lq + q0 + row;
+    a.lse[idx] = lse;
+    a.delta[idx] = delta;
+  }
+
+  // ---- pass 2: dq ----------------------------------------------------------------------------
+  wm::fragment<wm::accumulator, 16, 16, 16, float> dq[4];
+  acc_zero(dq);
+  for (int k0 = 0; k0 < a.Lk; k0 += kAB) {
+    __syncthreads();
+    attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
+    attn_load_block(sm.v, a.v, a.ldv, k0, a.Lk, kbase, h * 64);
+    attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
+    __syncthreads();
+    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
+    acc_zero(acc);
+    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);
+    acc_store(acc, &sm.s[warp * 16][0]);
+    acc_zero(acc);
+    mm_a_bt(acc, &sm.dO[warp * 16][0], sm.v);
+    acc_store(acc, &sm.dp[warp * 16][0]);
+    __syncwarp();
+#pragma unroll 8
+    for (int j = 0; j < 32; j += 2) {
+      const float p0 = __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - lse);
+      const float p1 = __expf(sm.s[row][cbeg + j + 1] * kAttScale + sm.bias[cbeg + j + 1] - lse);
+      const float d0 = p0 * (sm.dp[row][cbeg + j] - delta), d1 = p1 * (sm.dp[row][cbeg + j + 1] - delta);
+      *reinterpret_cast<uint32_t*>(&sm.ds[row][cbeg + j]) = pack_bf16x2(d0, d1);
+    }
+    __syncwarp();
+    mm_a_b(dq, &sm.ds[warp * 16][0], sm.k);
+  }
+  __syncwarp();
+  acc_store(dq, &sm.s[warp * 16][0]);
+  __syncwarp();
+  if (q0 + row < a.Lq) {
+    bf16* pq = a.dq + (qbase + q0 + row) * a.lddq + h * 64 + cbeg;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2)
+      *reinterpret_cast<uint32_t*>(pq + j) = pack_bf16x2(sm.s[row][cbeg + j] * kAttScale, sm.s[row][cbeg + j + 1] * kAttScale);
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_raw);
+  const int k0 = blockIdx.x * kAB, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = warp * 16 + (lane >> 1);
+  const int cbeg = (lane & 1) * 32;
+  const int64_t qbase = static_cast<int64_t>(b) * a.Lq, kbase = static_cast<int64_t>(b) * a.Lk;
+
+  attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
+  attn_load_block(sm.v, a.v, a.ldv, k0, a.Lk, kbase, h * 64);
+  attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
+  wm::fragment<wm::accumulator, 16, 16, 16, float> dk[4], dv[4];
+  acc_zero(dk);
+  acc_zero(dv);
+  for (int q0 = 0; q0 < a.Lq; q0 += kAB) {
+    __syncthreads();
+    attn_load_block(sm.q, a.q, a.ldq, q0, a.Lq, qbase, h * 64);
+    attn_load_block(sm.dO, a.dO, a.lddo, q0, a.Lq, qbase, h * 64);
+    for (int j = threadIdx.x; j < kAB; j += blockDim.x) {
+      const bool ok = q0 + j < a.Lq;
+      const int64_t idx = (static_cast<int64_t>(b) * a.H + h) * a.Lq + q0 + j;
+      sm.lse[j] = ok ? a.lse[idx] : INFINITY;          // rows beyond Lq: p = exp(-inf) = 0
+      sm.delta[j] = ok ? a.delta[idx] : 0.f;
+    }
+    __syncthreads();
+    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
+    acc_zero(acc);
+    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);          // s[query, key]
+    acc_store(acc, &sm.s[warp * 16][0]);
+    acc_zero(acc);
+    mm_a_bt(acc, &sm.dO[warp * 16][0], sm.v);         // dp[query, key]
+    acc_store(acc, &sm.dp[warp * 16][0]);
+    __syncwarp();
+    const float lse = sm.lse[row], delta = sm.delta[row];
+#pragma unroll 8
+    for (int j = 0; j < 32; j += 2) {
+      const float p0 = __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - lse);
+      const float p1 = __expf(sm.s[row][cbeg + j + 1] * kAttScale + sm.bias[cbeg + j + 1] - lse);
+      const float d0 = p0 * (sm.dp[row][cbeg + j] - delta), d1 = p1 * (sm.dp[row][cbeg + j + 1] - delta);
+      *reinterpret_cast<uint32_t*>(&sm.p[row][cbeg + j]) = pack_bf16x2(p0, p1);
+      *reinterpret_cast<uint32_t*>(&sm.ds[row][cbeg + j]) = pack_bf16x2(d0, d1);
+    }
+    __syncthreads();
+    mm_at_b(dv, sm.p, warp * 16, sm.dO);              // dv[key, :] += p^T do
+    mm_at_b(dk, sm.ds, warp * 16, sm.q);              // dk[key, :] += ds^T q
+  }
+  __syncthreads();
+  acc_store(dv, &sm.s[warp * 16][0]);
+  acc_store(dk, &sm.dp[warp * 16][0]);
+  __syncwarp();
+  if (k0 + row < a.Lk) {
+    bf16* pv = a.dv + (kbase + k0 + row) * a.lddv + h * 64 + cbeg;
+    bf16* pk = a.dk + (kbase + k0 + row) * a.lddk + h * 64 + cbeg;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      *reinterpret_cast<uint32_t*>(pv + j) = pack_bf16x2(sm.s[row][cbeg + j], sm.s[row][cbeg + j + 1]);
+      *reinterpret_cast<uint32_t*>(pk + j) = pack_bf16x2(sm.dp[row][cbeg + j] * kAttScale, sm.dp[row][cbeg + j + 1] * kAttScale);
+    }
+  }
+}
+
+static int elementwise_blocks(size_t n, int per_block) {
+  size_t blocks = (n + per_block - 1) / per_block;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace tanb
+
+using namespace tanb;
+
+extern "C" int tan_transpose_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int R_pad,
+                                  void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (in == nullptr || out == nullptr) return set_error(TAN_ERR_ARG, "tan_transpose_bf16: null pointer");
+  if (R <= 0 || C <= 0 || C % 2 != 0 || R_pad < R || R_pad % 2 != 0 || ldi < C || ldo < R_pad || ldi % 2 != 0 ||
+      ldo % 2 != 0)
+    return set_error(TAN_ERR_SHAPE, "tan_transpose_bf16: need even C / R_pad / pitches, R_pad >= R (R=%d C=%d R_pad=%d)",
+                     R, C, R_pad);
+  if ((reinterpret_cast<uintptr_t>(in) & 3) || (reinterpret_cast<uintptr_t>(out) & 3))
+    return set_error(TAN_ERR_SHAPE, "tan_transpose_bf16: pointers must be 4-byte aligned");
+  dim3 grid((R_pad + 63) / 64, (C + 63) / 64);
+  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(in), ldi, static_cast<bf16*>(out), ldo, R, C, R_pad);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+static int colsum_slabs(int M) {
+  int slabs = (M + 511) / 512;
+  if (slabs > 64) slabs = 64;
+  return slabs < 1 ? 1 : slabs;
+}
+
+extern "C" size_t tan_colsum_workspace_bytes(int M, int N) {
+  return static_cast<size_t>(colsum_slabs(M)) * static_cast<size_t>(N) * sizeof(float);
+}
+
+extern "C" int tan_colsum(const void* in, int in_is_bf16, int64_t ld, int M, int N, float* out, int accumulate,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (in == nullptr || out == nullptr) return set_error(TAN_ERR_ARG, "tan_colsum: null pointer");
+  if (M <= 0 || N <= 0 || N % 2 != 0 || ld < N || ld % 2 != 0)
+    return set_error(TAN_ERR_SHAPE, "tan_colsum: need M > 0, even N and pitch (M=%d N=%d)", M, N);
+  if (workspace == nullptr || workspace_bytes < tan_colsum_workspace_bytes(M, N))
+    return set_error(TAN_ERR_WORKSPACE, "tan_colsum: workspace too small");
+  const int slabs = colsum_slabs(M);
+  const int rows_per_slab = (M + slabs - 1) / slabs;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((N + 63) / 64, slabs);
+  float* partial = static_cast<float*>(workspace);
+  if (in_is_bf16)
+    colsum_partial_kernel<true><<<grid, 256, 0, st>>>(in, ld, M, N, rows_per_slab, partial);
+  else
+    colsum_partial_kernel<false><<<grid, 256, 0, st>>>(in, ld, M, N, rows_per_slab, partial);
+  TAN_CUDA(cudaGetLastError());
+  colsum_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, slabs, N, out, accumulate);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_quickgelu_fwd(const void* u, void* h, size_t n, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (u == nullptr || h == nullptr) return set_error(TAN_ERR_ARG, "tan_quickgelu_fwd: null pointer");
+  if (n % 8 != 0 || (reinterpret_cast<uintptr_t>(u) & 15) || (reinterpret_cast<uintptr_t>(h) & 15))
+    return set_error(TAN_ERR_SHAPE, "tan_quickgelu_fwd: n %% 8 == 0 and 16-byte aligned pointers required");
+  if (n == 0) return TAN_OK;
+  quickgelu_fwd_kernel<<<elementwise_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(u), static_cast<uint4*>(h), n / 8);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_quickgelu_bwd(const void* dh, const void* u, void* du, size_t n, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (dh == nullptr || u == nullptr || du == nullptr) return set_error(TAN_ERR_ARG, "tan_quickgelu_bwd: null pointer");
+  if (n % 8 != 0 || (reinterpret_cast<uintptr_t>(u) & 15) || (reinterpret_cast<uintptr_t>(dh) & 15) ||
+      (reinterpret_cast<uintptr_t>(du) & 15))
+    return set_error(TAN_ERR_SHAPE, "tan_quickgelu_bwd: n %% 8 == 0 and 16-byte aligned pointers required");
+  if (n == 0) return TAN_OK;
+  quickgelu_bwd_kernel<<<elementwise_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dh), static_cast<const uint4*>(u), static_cast<uint4*>(du), n / 8);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+static int ln_bwd_blocks(int rows) {
+  int blocks = (rows + 7) / 8;
+  const int cap = num_sms() * 2;
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
+}
+
+extern "C" size_t tan_layernorm_bwd_workspace_bytes(int rows, int d) {
+  return static_cast<size_t>(ln_bwd_blocks(rows)) * 2 * static_cast<size_t>(d) * sizeof(float);
+}
+
+extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate_dx,
+                                 int rows, int d, int L_in, int L_out, int l_off, float* dgamma, float* dbeta,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (dy == nullptr || x == nullptr || dx == nullptr) return set_error(TAN_ERR_ARG, "tan_layernorm_bwd: null pointer");
+  if (rows <= 0) return TAN_OK;
+  if (d % 128 != 0 || d <= 0 || d > 1024)
+    return set_error(TAN_ERR_SHAPE, "tan_layernorm_bwd: d must be a multiple of 128 and <= 1024 (d=%d)", d);
+  if (L_in <= 0 || L_out < L_in + l_off || l_off < 0)
+    return set_error(TAN_ERR_SHAPE, "tan_layernorm_bwd: bad row map (L_in=%d L_out=%d l_off=%d)", L_in, L_out, l_off);
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(TAN_ERR_ARG, "tan_layernorm_bwd: dgamma/dbeta mismatch");
+  const int blocks = ln_bwd_blocks(rows);
+  float* partial = nullptr;
+  if (dgamma != nullptr) {
+    if (workspace == nullptr || workspace_bytes < tan_layernorm_bwd_workspace_bytes(rows, d))
+      return set_error(TAN_ERR_WORKSPACE, "tan_layernorm_bwd: workspace too small");
+    partial = static_cast<float*>(workspace);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TAN_LNB(V)                                                                                              \
+  layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gamma, dx, accumulate_dx, rows, d, L_in, L_out, l_off, \
+                                                  partial)
+  switch (d / 128) {
+    case 1: TAN_LNB(1); break;
+    case 2: TAN_LNB(2); break;
+    case 3: TAN_LNB(3); break;
+    case 4: TAN_LNB(4); break;
+    case 5: TAN_LNB(5); break;
+    case 6: TAN_LNB(6); break;
+    case 7: TAN_LNB(7); break;
+    default: TAN_LNB(8); break;
+  }
+#undef TAN_LNB
+  TAN_CUDA(cudaGetLastError());
+  if (dgamma != nullptr) {
+    ln_param_finish_kernel<<<(d + 255) / 256, 256, 0, st>>>(partial, blocks, d, dgamma, dbeta);
+    TAN_CUDA(cudaGetLastError());
+  }
+  return TAN_OK;
+}
+
+extern "C" int tan_l2norm_bwd(const float* x, const float* g, float* dst, int accumulate, int rows, int d, int L_in,
+                              int64_t src_stride, int L_out, int l_off, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (x == nullptr || g == nullptr || dst == nullptr) return set_error(TAN_ERR_ARG, "tan_l2norm_bwd: null pointer");
+  if (rows <= 0) return TAN_OK;
+  if (d % 128 != 0 || d <= 0 || d > 1024)
+    return set_error(TAN_ERR_SHAPE, "tan_l2norm_bwd: d must be a multiple of 128 and <= 1024 (d=%d)", d);
+  if (L_in <= 0 || src_stride < L_in || L_out < L_in + l_off || l_off < 0)
+    return set_error(TAN_ERR_SHAPE, "tan_l2norm_bwd: bad row maps");
+  int blocks = (rows + 7) / 8;
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define TAN_L2B(V) \
+  l2norm_bwd_kernel<V><<<blocks, 256, 0, st>>>(x, g, dst, accumulate, rows, d, L_in, src_stride, L_out, l_off)
+  switch (d / 128) {
+    case 1: TAN_L2B(1); break;
+    case 2: TAN_L2B(2); break;
+    case 3: TAN_L2B(3); break;
+    case 4: TAN_L2B(4); break;
+    case 5: TAN_L2B(5); break;
+    case 6: TAN_L2B(6); break;
+    case 7: TAN_L2B(7); break;
+    default: TAN_L2B(8); break;
+  }
+#undef TAN_L2B
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_batch_sum(const float* in, float* out, int B, int L, int d, int L_out, int l_off, int accumulate,
+                             void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (in == nullptr || out == nullptr) return set_error(TAN_ERR_ARG, "tan_batch_sum: null pointer");
+  if (B <= 0 || L <= 0 || d <= 0 || L_out < L + l_off || l_off < 0)
+    return set_error(TAN_ERR_SHAPE, "tan_batch_sum: bad shape");
+  batch_sum_kernel<<<elementwise_blocks(static_cast<size_t>(L) * d, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, B, L, d, L_out, l_off, accumulate);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pad, int r0, const tan_sim_geom* g,
+                                  const uint32_t* posbits, const uint8_t* col_valid, const uint8_t* row_kill,
+                                  const float* ra, const float* rap, const float* cb, const float* cbp, void* G,
+                                  int64_t ldg, void* GT, int64_t ldgt, void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (z == nullptr || g == nullptr || posbits == nullptr || col_valid == nullptr || ra == nullptr || rap == nullptr ||
+      cb == nullptr || cbp == nullptr || G == nullptr || GT == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_sim_grad_tiles: null pointer");
+  const int C = g->C;
+  const int Cp = static_cast<int>(ldg);
+  if (Rc <= 0 || Rc_pad < Rc || Rc_pad % 2 != 0 || C <= 0 || C % 2 != 0 || ldz < C || ldz % 2 != 0 || ldg < C ||
+      ldg % 2 != 0 || ldgt < Rc_pad || ldgt % 2 != 0 || r0 < 0 || r0 + Rc > g->B_loc * g->T)
+    return set_error(TAN_ERR_SHAPE, "tan_sim_grad_tiles: bad shape (Rc=%d Rc_pad=%d C=%d r0=%d)", Rc, Rc_pad, C, r0);
+  dim3 grid((Rc_pad + 63) / 64, (Cp + 63) / 64);
+  sim_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, ldz, Rc, Rc_pad, C, Cp, r0, g->T, g->N, (g->N + 31) / 32, g->b_off, posbits, col_valid, row_kill, ra, rap, cb,
+      cbp, static_cast<bf16*>(G), ldg, static_cast<bf16*>(GT), ldgt);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}
+
+extern "C" int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                      const void* o, int64_t ldo, const void* d_out, int64_t lddo,
+                                      const uint8_t* key_padding_mask, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                                      void* dv, int64_t lddv, float* lse, float* delta, int B, int H, int Lq, int Lk,
+                                      void* stream) {
+  TAN_CHECK(tan_device_check());
+  if (q == nullptr || k == nullptr || v == nullptr || o == nullptr || d_out == nullptr || dq == nullptr ||
+      dk == nullptr || dv == nullptr || lse == nullptr || delta == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_attention_bwd_bf16: null pointer");
+  if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0 || B > 65535 || H > 65535)
+    return set_error(TAN_ERR_SHAPE, "tan_attention_bwd_bf16: bad dims (B=%d H=%d Lq=%d Lk=%d)", B, H, Lq, Lk);
+  const int64_t lds[8] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv};
+  const void* ptrs[8] = {q, k, v, o, d_out, dq, dk, dv};
+  for (int i = 0; i < 8; ++i)
+    if (lds[i] % 8 != 0 || lds[i] < static_cast<int64_t>(H) * 64 || (reinterpret_cast<uintptr_t>(ptrs[i]) & 15))
+      return set_error(TAN_ERR_SHAPE, "tan_attention_bwd_bf16: operands need 16-byte aligned bases, pitches %% 8 == 0 and >= 64 H");
+  AttnBwdArgs a;
+  a.q = static_cast<const bf16*>(q); a.ldq = ldq;
+  a.k = static_cast<const bf16*>(k); a.ldk = ldk;
+  a.v = static_cast<const bf16*>(v); a.ldv = ldv;
+  a.o = static_cast<const bf16*>(o); a.ldo = ldo;
+  a.dO = static_cast<const bf16*>(d_out); a.lddo = lddo;
+  a.kpm = key_padding_mask;
+  a.dq = static_cast<bf16*>(dq); a.lddq = lddq;
+  a.dk = static_cast<bf16*>(dk); a.lddk = lddk;
+  a.dv = static_cast<bf16*>(dv); a.lddv = lddv;
+  a.lse = lse; a.delta = delta;
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  const int smem = static_cast<int>(sizeof(AttnBwdSmem)) + 128;
+  TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  attn_bwd_dq_kernel<<<dim3((Lq + kAB - 1) / kAB, H, B), 128, smem, st>>>(a);
+  TAN_CUDA(cudaGetLastError());
+  attn_bwd_dkv_kernel<<<dim3((Lk + kAB - 1) / kAB, H, B), 128, smem, st>>>(a);
+  TAN_CUDA(cudaGetLastError());
+  return TAN_OK;
+}

@@ -314,3 +314,120 @@ def agree_targets(old_posbits, win_joint, win_dual, replace_u8, B: int, T: int, 
           "tan_agree_targets")
     _launches += 1
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# backward pass (training step)
+# ------------------------------------------------------------------------------------------------------
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def transpose_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """tan_transpose_bf16: x [R, C] bf16 (row pitch may exceed C) -> [C, pad64(R)] with zero padding."""
+    global _launches
+    R, Ccols = x.shape
+    Rp = pad64(R)
+    if out is None:
+        out = torch.empty(Ccols, Rp, dtype=torch.bfloat16, device=x.device)
+    if _skip("bwd_glue", 2.0 * R * Ccols):
+        return out
+    check(lib().tan_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, Ccols, Rp, _stream()),
+          "tan_transpose_bf16")
+    _launches += 1
+    return out
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = True) -> None:
+    """tan_colsum: out [N] fp32 (+)= column sums of x [M, N] (bf16 or fp32)."""
+    global _launches
+    M, N = x.shape
+    if _skip("bwd_glue", float(M) * N):
+        return
+    nbytes = int(lib().tan_colsum_workspace_bytes(M, N))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib().tan_colsum(x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), M, N, out.data_ptr(),
+                           int(bool(accumulate)), ws.data_ptr(), nbytes, _stream()), "tan_colsum")
+    _launches += 2
+
+
+def quickgelu_fwd(u: torch.Tensor, h: torch.Tensor) -> None:
+    global _launches
+    if _skip("bwd_glue", float(u.numel())):
+        return
+    check(lib().tan_quickgelu_fwd(u.data_ptr(), h.data_ptr(), u.numel(), _stream()), "tan_quickgelu_fwd")
+    _launches += 1
+
+
+def quickgelu_bwd(dh: torch.Tensor, u: torch.Tensor, du: torch.Tensor) -> None:
+    global _launches
+    if _skip("bwd_glue", float(u.numel())):
+        return
+    check(lib().tan_quickgelu_bwd(dh.data_ptr(), u.data_ptr(), du.data_ptr(), u.numel(), _stream()),
+          "tan_quickgelu_bwd")
+    _launches += 1
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: torch.Tensor, accumulate_dx: bool,
+                  rows: int, d: int, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
+                  L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0) -> None:
+    """tan_layernorm_bwd (dy, x, dx fp32; dgamma / dbeta accumulated)."""
+    global _launches
+    L_in = rows if L_in is None else L_in
+    L_out = L_in if L_out is None else L_out
+    if _skip("bwd_glue", float(rows) * d):
+        return
+    nbytes = int(lib().tan_layernorm_bwd_workspace_bytes(rows, d))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib().tan_layernorm_bwd(dy.data_ptr(), x.data_ptr(), _ptr(gamma), dx.data_ptr(), int(bool(accumulate_dx)),
+                                  rows, d, L_in, L_out, l_off, _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), nbytes,
+                                  _stream()), "tan_layernorm_bwd")
+    _launches += 2
+
+
+def l2norm_bwd(x: torch.Tensor, g: torch.Tensor, dst: torch.Tensor, accumulate: bool, rows: int, d: int, L_in: int,
+               src_stride: int, L_out: int, l_off: int) -> None:
+    """tan_l2norm_bwd; x / g are views whose data_ptr() is the stage's first row."""
+    global _launches
+    if _skip("bwd_glue", float(rows) * d):
+        return
+    check(lib().tan_l2norm_bwd(x.data_ptr(), g.data_ptr(), dst.data_ptr(), int(bool(accumulate)), rows, d, L_in,
+                               src_stride, L_out, l_off, _stream()), "tan_l2norm_bwd")
+    _launches += 1
+
+
+def batch_sum(x: torch.Tensor, out: torch.Tensor, B: int, L: int, d: int, L_out: int, l_off: int,
+              accumulate: bool) -> None:
+    global _launches
+    if _skip("bwd_glue", float(B) * L * d):
+        return
+    check(lib().tan_batch_sum(x.data_ptr(), out.data_ptr(), B, L, d, L_out, l_off, int(bool(accumulate)), _stream()),
+          "tan_batch_sum")
+    _launches += 1
+
+
+def sim_grad_tiles(z: torch.Tensor, Rc: int, r0: int, g: SimGeom, posbits, col_valid, row_kill, ra, rap, cb, cbp,
+                   G: torch.Tensor, GT: torch.Tensor) -> None:
+    """tan_sim_grad_tiles: z [Rc, >=C] fp32 -> G [Rc, Cp] bf16, GT [C, pad64(Rc)] bf16."""
+    global _launches
+    if _skip("bwd_glue", float(Rc) * g.C):
+        return
+    check(lib().tan_sim_grad_tiles(z.data_ptr(), z.stride(0), Rc, pad64(Rc), r0, C.byref(g), posbits.data_ptr(),
+                                   col_valid.data_ptr(), _ptr(row_kill), ra.data_ptr(), rap.data_ptr(), cb.data_ptr(),
+                                   cbp.data_ptr(), G.data_ptr(), G.stride(0), GT.data_ptr(), GT.stride(0), _stream()),
+          "tan_sim_grad_tiles")
+    _launches += 1
+
+
+def attention_bwd(q, k, v, o, d_out, kpm_u8, dq, dk, dv, lse, delta, B: int, H: int, Lq: int, Lk: int) -> None:
+    """tan_attention_bwd_bf16 (2-D, possibly column-sliced bf16 views as in `attention`)."""
+    global _launches
+    if _skip("attention_bwd", 10.0 * B * H * Lq * Lk * 64):
+        return
+    with _timed("attention_bwd", 10.0 * B * H * Lq * Lk * 64):
+        check(lib().tan_attention_bwd_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                           v.stride(0), o.data_ptr(), o.stride(0), d_out.data_ptr(), d_out.stride(0),
+                                           _ptr(kpm_u8), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0),
+                                           dv.data_ptr(), dv.stride(0), lse.data_ptr(), delta.data_ptr(), B, H, Lq, Lk,
+                                           _stream()), "tan_attention_bwd_bf16")
+    _launches += 2
