@@ -303,11 +303,12 @@ TAN_API int tan_layernorm_bwd(const float* dy, const float* x, const float* gamm
                               int rows, int d, int L_in, int L_out, int l_off, float* dgamma, float* dbeta,
                               void* workspace, size_t workspace_bytes, void* stream);
 
-/* Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137): dst = (g - y <y, g>) / ||x||.  x and g share the
- * stage-feature layout (row r at (r / L_in) * src_stride + r % L_in), dst is token-major (row
- * (r / L_in) * L_out + l_off + r % L_in); written, or added when accumulate != 0.  fp32. */
+/* Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137): dst = (g - y <y, g>) / ||x||.  Row r of the raw
+ * features x lies at (r / L_in) * src_stride + r % L_in, of the incoming gradient g at (r / L_in) * g_stride +
+ * r % L_in; dst is token-major (row (r / L_in) * L_out + l_off + r % L_in); written, or added when
+ * accumulate != 0.  fp32. */
 TAN_API int tan_l2norm_bwd(const float* x, const float* g, float* dst, int accumulate, int rows, int d, int L_in,
-                           int64_t src_stride, int L_out, int l_off, void* stream);
+                           int64_t src_stride, int64_t g_stride, int L_out, int l_off, void* stream);
 
 /* out[l, :] (+)= sum_b in[b * L_out + l_off + l, :]: gradient of a positional table broadcast over the clips
  * (model/tan_model.py:161-167).  fp32. */

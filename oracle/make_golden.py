@@ -187,6 +187,47 @@ def run_loss_cases():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "g_loss_full.npz"), **out)
 
 
+# parameter-gradient fixtures (training step): name -> (model case, loss-arg overrides).  The alignability head is
+# switched off (its BCE branch is not differentiated by the CUDA path yet).
+GRAD_CASES = {
+    "g1": ("g1_e1d1_T32_B4", {}),
+    "g2": ("g2_e2d3_T24_B3", {}),
+    "g2_thr": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5)),
+    "g3": ("g3_e6d6_T64_B2", {}),
+}
+GRAD_STRIDE = 997        # every 997th element of each parameter gradient is stored (+ its norm)
+
+
+def run_param_grads():
+    """d loss / d parameter of the UNMODIFIED reference (forward + get_loss + autograd, fp32 CPU): per parameter
+    the gradient norm and a strided subsample -> tests/golden/g_param_grads.npz.  Pins the oracle's autograd
+    (tests/test_oracle.py), which in turn is what the GPU backward pass is checked against."""
+    tfm, tan, ref_loss = load_reference()
+    out = {}
+    for tag, (case, kw) in GRAD_CASES.items():
+        cfg = CASES[case]
+        m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], 0)
+        m.train()
+        batch = synth.make_batch(cfg["B"], cfg["T"], cfg["N"], pad_video_every=cfg["pad_video_every"])
+        video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+        vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+        res = m(video, text, vpm, tpm, None)
+        input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
+        loss = ref_loss.get_loss(input_data, video, text, vpm.float(), tpm.float(), res, loss_args(**kw), None)
+        loss["loss"].backward()
+        out[f"{tag}/loss"] = np.array(float(loss["loss"]))
+        n = 0
+        for name, p in m.named_parameters():
+            if name.startswith("bert.") or p.grad is None:
+                continue
+            g = p.grad.detach().double().reshape(-1)
+            out[f"{tag}/norm/{name}"] = np.array(float(g.norm()))
+            out[f"{tag}/sub/{name}"] = g[::GRAD_STRIDE].float().numpy()
+            n += 1
+        print("param grads", tag, float(loss["loss"]), n, "parameters")
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_param_grads.npz"), **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -203,6 +244,8 @@ def main():
         run_blocks()
     if not a.only or a.only == "g_loss_full":
         run_loss_cases()
+    if not a.only or a.only == "g_param_grads":
+        run_param_grads()
 
 
 if __name__ == "__main__":

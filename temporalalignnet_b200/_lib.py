@@ -96,7 +96,7 @@ SIGNATURES = {
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                     C.c_void_p]),
     "tan_l2norm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
-                                 C.c_int, C.c_int, C.c_void_p]),
+                                 C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "tan_batch_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p]),
     "tan_sim_grad_tiles": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(SimGeom), C.c_void_p,

@@ -245,23 +245,25 @@ __global__ void ln_param_finish_kernel(const float* __restrict__ partial, int bl
 
 // ------------------------------------------------------------------------------------------------
 // Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137) with row maps on both sides:
-//   src row (raw features x and incoming gradient g):  (r / L_in) * src_stride + r % L_in
+//   src row of the raw features x: (r / L_in) * src_stride + r % L_in;  of the incoming gradient g: ... * g_stride ...
 //   dst row (token-major gradient buffer):            (r / L_in) * L_out + l_off + r % L_in
 //   dst = (g - y * <y, g>) / ||x||        (written, or added when accumulate != 0)
 // ------------------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                          float* __restrict__ dst, int accumulate, int rows, int d,
-                                                         int L_in, int64_t src_stride, int L_out, int l_off) {
+                                                         int L_in, int64_t src_stride, int64_t g_stride, int L_out,
+                                                         int l_off) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
     const int b = r / L_in, l = r - b * L_in;
     const int64_t sr = static_cast<int64_t>(b) * src_stride + l;
+    const int64_t gr = static_cast<int64_t>(b) * g_stride + l;
     const int64_t dr = static_cast<int64_t>(b) * L_out + l_off + l;
     float xv[V * 4], gv[V * 4];
     const float4* px = reinterpret_cast<const float4*>(x + sr * d);
-    const float4* pg = reinterpret_cast<const float4*>(g + sr * d);
+    const float4* pg = reinterpret_cast<const float4*>(g + gr * d);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const float4 a = px[i * 32 + lane], c = pg[i * 32 + lane];
@@ -797,20 +799,20 @@ extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* g
 }
 
 extern "C" int tan_l2norm_bwd(const float* x, const float* g, float* dst, int accumulate, int rows, int d, int L_in,
-                              int64_t src_stride, int L_out, int l_off, void* stream) {
+                              int64_t src_stride, int64_t g_stride, int L_out, int l_off, void* stream) {
   TAN_CHECK(tan_device_check());
   if (x == nullptr || g == nullptr || dst == nullptr) return set_error(TAN_ERR_ARG, "tan_l2norm_bwd: null pointer");
   if (rows <= 0) return TAN_OK;
   if (d % 128 != 0 || d <= 0 || d > 1024)
     return set_error(TAN_ERR_SHAPE, "tan_l2norm_bwd: d must be a multiple of 128 and <= 1024 (d=%d)", d);
-  if (L_in <= 0 || src_stride < L_in || L_out < L_in + l_off || l_off < 0)
+  if (L_in <= 0 || src_stride < L_in || g_stride < L_in || L_out < L_in + l_off || l_off < 0)
     return set_error(TAN_ERR_SHAPE, "tan_l2norm_bwd: bad row maps");
   int blocks = (rows + 7) / 8;
   const int cap = num_sms() * 8;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TAN_L2B(V) \
-  l2norm_bwd_kernel<V><<<blocks, 256, 0, st>>>(x, g, dst, accumulate, rows, d, L_in, src_stride, L_out, l_off)
+  l2norm_bwd_kernel<V><<<blocks, 256, 0, st>>>(x, g, dst, accumulate, rows, d, L_in, src_stride, g_stride, L_out, l_off)
   switch (d / 128) {
     case 1: TAN_L2B(1); break;
     case 2: TAN_L2B(2); break;
@@ -848,7 +850,7 @@ extern "C" int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pa
     return set_error(TAN_ERR_ARG, "tan_sim_grad_tiles: null pointer");
   const int C = g->C;
   const int Cp = static_cast<int>(ldg);
-  if (Rc <= 0 || Rc_pad < Rc || Rc_pad % 2 != 0 || C <= 0 || C % 2 != 0 || ldz < C || ldz % 2 != 0 || ldg < C ||
+  if (Rc <= 0 || Rc_pad < Rc || Rc_pad % 2 != 0 || C <= 0 || ldz < C + (C & 1) || ldz % 2 != 0 || ldg < C + (C & 1) ||
       ldg % 2 != 0 || ldgt < Rc_pad || ldgt % 2 != 0 || r0 < 0 || r0 + Rc > g->B_loc * g->T)
     return set_error(TAN_ERR_SHAPE, "tan_sim_grad_tiles: bad shape (Rc=%d Rc_pad=%d C=%d r0=%d)", Rc, Rc_pad, C, r0);
   dim3 grid((Rc_pad + 63) / 64, (Cp + 63) / 64);

@@ -326,6 +326,21 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     dist = _dist() if shard else None
     nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard)
     loss_dict = {}
+    # training step: the forward ran with a tape (model.enable_autograd) -> the returned loss carries ONE autograd
+    # node whose backward is the hand-written backward pass (train.py)
+    tape = getattr(logits_dual, "tape", None) if isinstance(logits_dual, LazyLogits) else None
+    want_grad = tape is not None and torch.is_grad_enabled()
+    if want_grad and not (learn or thr > 0 or head):
+        from . import train
+        rs_d, cs_d, _ = nce_sums_one_model(logits_dual, nce, shard)
+        rs_j, cs_j, _ = nce_sums_one_model(logits_joint, nce, shard)
+        loss_dual = finish_loss(rs_d, cs_d, dist, T, reduce_cols=False)
+        loss_joint = finish_loss(rs_j, cs_j, dist, T, reduce_cols=False)
+        loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
+        loss_dict['loss'] = train.attach_autograd((loss_dual + loss_joint) / 2, tape,
+                                                  train.SimCtx(logits_dual, rs_d, cs_d, nce),
+                                                  train.SimCtx(logits_joint, rs_j, cs_j, nce), 1.0, dist)
+        return loss_dict
     if not (learn or thr > 0 or head):
         loss_dual, loss_joint = nce_losses_pair(logits_dual, logits_joint, nce, shard)
         loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
@@ -374,6 +389,7 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
     loss_th = None
     loss_bce = None
+    row_sel = col_sel = None
     if thr > 0 or head:
         # ---- keep the most alignable sentences (train/loss.py:277-304) -----------------------------
         if md is None:
@@ -420,5 +436,9 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
         loss = (loss_dual + loss_joint) / 2
     if head:
         loss = loss * nce_weight + loss_bce
+    if want_grad:
+        from . import train
+        loss = train.attach_autograd(loss, tape, train.SimCtx(logits_dual, rs_d, cs_d, nce, row_sel, col_sel),
+                                     train.SimCtx(logits_joint, rs_j, cs_j, nce, row_sel, col_sel), nce_weight, dist)
     loss_dict['loss'] = loss
     return loss_dict

@@ -386,13 +386,14 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: to
 
 
 def l2norm_bwd(x: torch.Tensor, g: torch.Tensor, dst: torch.Tensor, accumulate: bool, rows: int, d: int, L_in: int,
-               src_stride: int, L_out: int, l_off: int) -> None:
+               src_stride: int, L_out: int, l_off: int, g_stride: Optional[int] = None) -> None:
     """tan_l2norm_bwd; x / g are views whose data_ptr() is the stage's first row."""
     global _launches
     if _skip("bwd_glue", float(rows) * d):
         return
     check(lib().tan_l2norm_bwd(x.data_ptr(), g.data_ptr(), dst.data_ptr(), int(bool(accumulate)), rows, d, L_in,
-                               src_stride, L_out, l_off, _stream()), "tan_l2norm_bwd")
+                               src_stride, src_stride if g_stride is None else g_stride, L_out, l_off, _stream()),
+          "tan_l2norm_bwd")
     _launches += 1
 
 

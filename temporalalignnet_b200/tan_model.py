@@ -171,6 +171,8 @@ class TemporalAligner(nn.Module):
         self._graphs = {}
         self._graphs_on = False
         self.two_streams = True      # run the dual and joint stacks concurrently (see forward)
+        from .train import AUTOGRAD_DEFAULT
+        self._autograd_on = AUTOGRAD_DEFAULT
 
     # the training driver calls `model.lang_model` (train/main.py:58) while the reference class
     # names it `bert` (model/tan_model.py:38-40); expose both
@@ -375,11 +377,27 @@ class TemporalAligner(nn.Module):
                 res[k] = LazyLogits(res[k].vfeat, res[k].tfeat, res[k].shared_text, res[k].N)
         return res
 
-    @torch.no_grad()
+    def enable_autograd(self, enabled: bool = True) -> None:
+        """Training step: while enabled, a `forward` called in train mode with grad enabled keeps the activations
+        (train.py) and `get_loss(...)['loss'].backward()` fills `.grad` of the parameters through the hand-written
+        backward pass.  Round-1 status: opt-in (TAN_AUTOGRAD=1 makes it the default), first correct path."""
+        self._autograd_on = bool(enabled)
+
     def forward(self, video_embed, lang_embed, video_padding_mask=None, lang_padding_mask=None,
                 text_timestamp=None, abs_text_pos=None, interpolate_from=None):
         """model/tan_model.py:100-149 (+ the `abs_text_pos` keyword train/main.py:86 passes)."""
         self._check_device(video_embed)
+        if (self._autograd_on and self.training and torch.is_grad_enabled()
+                and any(p.requires_grad for p in self.parameters())):
+            from . import train
+            with torch.no_grad():
+                return train.forward_train(self, video_embed, lang_embed, video_padding_mask, lang_padding_mask,
+                                           interpolate_from)
+        with torch.no_grad():
+            return self._forward_dispatch(video_embed, lang_embed, video_padding_mask, lang_padding_mask,
+                                          interpolate_from)
+
+    def _forward_dispatch(self, video_embed, lang_embed, video_padding_mask, lang_padding_mask, interpolate_from):
         if (self._graphs_on and not self.random_pos_start and not interpolate_from
                 and video_embed.dtype == torch.float32 and lang_embed.dtype == torch.float32 and lang_embed.is_cuda
                 and not torch.cuda.is_current_stream_capturing()):
@@ -613,6 +631,10 @@ class TwinTemporalAligner(nn.Module):
     def enable_cuda_graphs(self, enabled: bool = True) -> None:
         self.online.enable_cuda_graphs(enabled)
         self.target.enable_cuda_graphs(enabled)
+
+    def enable_autograd(self, enabled: bool = True) -> None:
+        """Only the online network trains (model/tan_model.py:334-338 freezes the target)."""
+        self.online.enable_autograd(enabled)
 
     def forward(self, *args, **kwargs):
         return self.online(*args, **kwargs)
