@@ -299,6 +299,11 @@ def run_gpu_arm(args):
     if rank == 0 and not args.skip_hbm:
         extra["roofline_nce_hbm"] = hbm_nce_roofline(runner, peaks, flush)
 
+    # ---- training step (forward with tape + get_loss + backward, no optimizer) ----------
+    # reported beside the headline metric, never as it: eager launches, 3 warm-up + `steps` timed steps
+    if world == 1 and not args.skip_train:
+        extra["train_step"] = train_step_leg(runner, min(steps, 5), flush, fl, tf_peak)
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         r = cpu_reference_clips_per_sec(3, 1)
@@ -320,6 +325,37 @@ def run_gpu_arm(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_leg(runner, steps, flush, fl, tf_peak):
+    """fwd + loss + bwd through the public API (`model(...)`, `get_loss`, `loss.backward()`), CUDA events per
+    step, L2 flushed between steps.  Algorithmic flops = 3 x the forward's (backward = 2 x forward)."""
+    import torch
+    try:
+        for _ in range(3):
+            runner.step_train()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = runner.step_train()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        ms = tot / steps
+        gn = sum(float(p.grad.float().norm() ** 2) for p in runner.model.parameters() if p.grad is not None) ** 0.5
+        for p in runner.model.parameters():
+            p.grad = None
+        tf = 3.0 * fl["total"] * runner.B / (ms * 1e-3) / 1e12
+        return {"value": round(runner.B / (ms * 1e-3), 1), "unit": "clips/s", "ms_per_step": round(ms, 3),
+                "steps": steps, "what": "forward (activations kept) + get_loss + loss.backward(), no optimizer; eager "
+                "launches; first correct backward path (DESIGN.md section 8)", "loss": round(float(loss), 6),
+                "grad_norm": round(gn, 6), "achieved": round(tf, 1), "peak": tf_peak, "unit_flops": "TFLOP/s",
+                "frac": round(tf / tf_peak, 4), "max_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    except Exception as e:                                   # never lose the headline line to the extra leg
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def hbm_nce_roofline(runner, peaks, flush):
@@ -374,6 +410,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-hbm", action="store_true", help="skip the materialised-logits HBM roofline leg")
+    ap.add_argument("--skip-train", action="store_true", help="skip the training-step (fwd+loss+bwd) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -328,6 +328,16 @@ TAN_API int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pad, 
                                const float* ra, const float* rap, const float* cb, const float* cbp, void* G,
                                int64_t ldg, void* GT, int64_t ldgt, void* stream);
 
+/* The similarity recomputation fused with tan_sim_grad_tiles: G [Rc, ldg] bf16 (columns g->C .. C_pad are zero) =
+ * d loss / d cos of rows r0 .. r0+Rc of one stage, computed in the epilogue of the tcgen05 pair GEMM
+ * <vfeat[r], tfeat[c]> (vfeat [Rc, d] bf16 (ldv), tfeat [C_pad, d] bf16 (ldt), rows beyond g->C zero) -- the
+ * fp32 cosines never reach HBM.  Same coefficient vectors / targets as tan_sim_grad_tiles; g->N <= 64,
+ * C_pad % 128 == 0, d % 64 == 0.  The transposed operand of dB is made with tan_transpose_bf16. */
+TAN_API int tan_sim_grad_gemm(const void* vfeat, int64_t ldv, const void* tfeat, int64_t ldt, int Rc, int r0,
+                              const tan_sim_geom* g, int C_pad, const uint32_t* posbits, const uint8_t* col_valid,
+                              const uint8_t* row_kill, const float* ra, const float* rap, const float* cb,
+                              const float* cbp, void* G, int64_t ldg, void* stream);
+
 /* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
  * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
  * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from

@@ -11,7 +11,10 @@
 // accumulators in TMEM is the follow-up.
 #include <mma.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "attn_bwd.cuh"
 
 namespace tanb {
 
@@ -330,40 +333,46 @@ __global__ void __launch_bounds__(256) sim_grad_kernel(const float* __restrict__
   const int rt = blockIdx.x * 64, ct = blockIdx.y * 64;
   constexpr float kInvTau = 1.0f / 0.07f;
   constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kK = kInvTau * kLog2e;
+  // this thread's two columns: validity and coefficients are loaded once
+  const int c = ct + 2 * tx;
+  bool cv[2];
+  float cbv[2], cbpv[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int cc = c + k;
+    cv[k] = cc < C && col_valid[cc] != 0;
+    cbv[k] = cv[k] ? cb[cc] : 0.f;
+    cbpv[k] = cv[k] ? cbp[cc] : 0.f;
+  }
+  const float invT = 1.0f / static_cast<float>(T);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rl = rt + ty + 8 * i;              // row inside the chunk
-    const int c = ct + 2 * tx;
-    float g0 = 0.f, g1 = 0.f;
+    float gv[2] = {0.f, 0.f};
     if (rl < Rc && c < C) {
       const int r = r0 + rl;                     // row of the stage: (b, t)
-      const int b = r / T, t = r - b * T;
+      const int b = __float2int_rd((static_cast<float>(r) + 0.5f) * invT);   // exact for r < 2^21
+      const int t = r - b * T;
       const float2 zz = *reinterpret_cast<const float2*>(z + static_cast<int64_t>(rl) * ldz + c);
       const float a = ra[r], ap = rap[r];
       const bool kill = row_kill != nullptr && row_kill[r] != 0;
-      const int own0 = (b_off + b) * N;
+      const int n0 = c - (b_off + b) * N;        // sentence index of column c inside the row's own clip
       const float zv[2] = {zz.x, zz.y};
-      float gv[2];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        const int cc = c + k;
-        float gg = 0.f;
-        if (cc < C && col_valid[cc] != 0) {
-          const int n = cc - own0;
-          const bool own = n >= 0 && n < N;
-          if (!(own && kill)) {
-            const float e = exp2f((zv[k] - 1.0f) * (kInvTau * kLog2e));
-            float coef = a + cb[cc];
-            if (own && ((posbits[(static_cast<int64_t>(b) * T + t) * W + (n >> 5)] >> (n & 31)) & 1u))
-              coef -= ap + cbp[cc];
-            gg = e * coef * kInvTau;
-          }
+        const int n = n0 + k;
+        const bool own = n >= 0 && n < N;
+        if (cv[k] && !(own && kill)) {
+          const float e = fast_exp2(fmaf(zv[k], kK, -kK));
+          float coef = a + cbv[k];
+          if (own && ((posbits[(static_cast<int64_t>(b) * T + t) * W + (n >> 5)] >> (n & 31)) & 1u))
+            coef -= ap + cbpv[k];
+          gv[k] = e * coef * kInvTau;
         }
-        gv[k] = gg;
       }
-      g0 = gv[0]; g1 = gv[1];
     }
-    const uint32_t packed = pack_bf16x2(g0, g1);
+    const uint32_t packed = pack_bf16x2(gv[0], gv[1]);
     tile[ty + 8 * i][2 * tx] = static_cast<uint16_t>(packed & 0xffffu);
     tile[ty + 8 * i][2 * tx + 1] = static_cast<uint16_t>(packed >> 16);
     if (rl < Rc && c < Cp) *reinterpret_cast<uint32_t*>(G + static_cast<int64_t>(rl) * ldg + c) = packed;
@@ -479,20 +488,6 @@ __device__ __forceinline__ void acc_store(const wm::fragment<wm::accumulator, 16
   for (int j = 0; j < 4; ++j) wm::store_matrix_sync(rows + j * 16, acc[j], kAF, wm::mem_row_major);
 }
 
-struct AttnBwdArgs {
-  const bf16* q; int64_t ldq;
-  const bf16* k; int64_t ldk;
-  const bf16* v; int64_t ldv;
-  const bf16* o; int64_t ldo;
-  const bf16* dO; int64_t lddo;
-  const uint8_t* kpm;
-  bf16* dq; int64_t lddq;
-  bf16* dk; int64_t lddk;
-  bf16* dv; int64_t lddv;
-  float* lse;      // [B, H, Lq]
-  float* delta;    // [B, H, Lq]
-  int B, H, Lq, Lk;
-};
 
 __device__ __forceinline__ void attn_fill_bias(float* bias, const uint8_t* kpm, int b, int Lk, int k0) {
   for (int j = threadIdx.x; j < kAB; j += blockDim.x) {
@@ -889,6 +884,8 @@ extern "C" int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k,
   a.dv = static_cast<bf16*>(dv); a.lddv = lddv;
   a.lse = lse; a.delta = delta;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+  static const bool use_wmma = [] { const char* e = getenv("TAN_ATTN_BWD"); return e != nullptr && e[0] == 'w'; }();
+  if (!use_wmma) return attention_bwd_mma(a, static_cast<cudaStream_t>(stream));
   const int smem = static_cast<int>(sizeof(AttnBwdSmem)) + 128;
   TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -113,15 +113,16 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
-           out_bf16: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE) -> None:
+           out_bf16: Optional[torch.Tensor] = None, act: int = _lib.ACT_NONE, tag: str = "linear") -> None:
     """out = act(a @ w.T + bias) [+ residual]  (tan_linear_bf16).  a [M,K] bf16 (row pitch may exceed
-    K), w [N,K] bf16; outputs 2-D with arbitrary row pitch."""
+    K), w [N,K] bf16; outputs 2-D with arbitrary row pitch.  `tag` names the kernel class in profiles
+    (forward projections: "linear"; backward: "dgrad", "wgrad", "sim_bwd")."""
     global _launches
     M, K = a.shape
     N = w.shape[0]
-    if _skip("linear", 2.0 * M * N * K):
+    if _skip(tag, 2.0 * M * N * K):
         return
-    with _timed("linear", 2.0 * M * N * K):
+    with _timed(tag, 2.0 * M * N * K):
         check(lib().tan_linear_bf16(
             a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
             _ptr(residual), residual.stride(0) if residual is not None else 0,
@@ -332,8 +333,9 @@ def transpose_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
         out = torch.empty(Ccols, Rp, dtype=torch.bfloat16, device=x.device)
     if _skip("bwd_glue", 2.0 * R * Ccols):
         return out
-    check(lib().tan_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, Ccols, Rp, _stream()),
-          "tan_transpose_bf16")
+    with _timed("transpose", 0.0):
+        check(lib().tan_transpose_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, Ccols, Rp, _stream()),
+              "tan_transpose_bf16")
     _launches += 1
     return out
 
@@ -346,8 +348,9 @@ def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = True) -> None:
         return
     nbytes = int(lib().tan_colsum_workspace_bytes(M, N))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    check(lib().tan_colsum(x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), M, N, out.data_ptr(),
-                           int(bool(accumulate)), ws.data_ptr(), nbytes, _stream()), "tan_colsum")
+    with _timed("colsum", 0.0):
+        check(lib().tan_colsum(x.data_ptr(), int(x.dtype == torch.bfloat16), x.stride(0), M, N, out.data_ptr(),
+                               int(bool(accumulate)), ws.data_ptr(), nbytes, _stream()), "tan_colsum")
     _launches += 2
 
 
@@ -355,7 +358,8 @@ def quickgelu_fwd(u: torch.Tensor, h: torch.Tensor) -> None:
     global _launches
     if _skip("bwd_glue", float(u.numel())):
         return
-    check(lib().tan_quickgelu_fwd(u.data_ptr(), h.data_ptr(), u.numel(), _stream()), "tan_quickgelu_fwd")
+    with _timed("gelu", 0.0):
+        check(lib().tan_quickgelu_fwd(u.data_ptr(), h.data_ptr(), u.numel(), _stream()), "tan_quickgelu_fwd")
     _launches += 1
 
 
@@ -363,8 +367,9 @@ def quickgelu_bwd(dh: torch.Tensor, u: torch.Tensor, du: torch.Tensor) -> None:
     global _launches
     if _skip("bwd_glue", float(u.numel())):
         return
-    check(lib().tan_quickgelu_bwd(dh.data_ptr(), u.data_ptr(), du.data_ptr(), u.numel(), _stream()),
-          "tan_quickgelu_bwd")
+    with _timed("gelu", 0.0):
+        check(lib().tan_quickgelu_bwd(dh.data_ptr(), u.data_ptr(), du.data_ptr(), u.numel(), _stream()),
+              "tan_quickgelu_bwd")
     _launches += 1
 
 
@@ -379,9 +384,10 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: to
         return
     nbytes = int(lib().tan_layernorm_bwd_workspace_bytes(rows, d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    check(lib().tan_layernorm_bwd(dy.data_ptr(), x.data_ptr(), _ptr(gamma), dx.data_ptr(), int(bool(accumulate_dx)),
-                                  rows, d, L_in, L_out, l_off, _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), nbytes,
-                                  _stream()), "tan_layernorm_bwd")
+    with _timed("ln_bwd", 0.0):
+        check(lib().tan_layernorm_bwd(dy.data_ptr(), x.data_ptr(), _ptr(gamma), dx.data_ptr(), int(bool(accumulate_dx)),
+                                      rows, d, L_in, L_out, l_off, _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), nbytes,
+                                      _stream()), "tan_layernorm_bwd")
     _launches += 2
 
 
@@ -391,9 +397,10 @@ def l2norm_bwd(x: torch.Tensor, g: torch.Tensor, dst: torch.Tensor, accumulate: 
     global _launches
     if _skip("bwd_glue", float(rows) * d):
         return
-    check(lib().tan_l2norm_bwd(x.data_ptr(), g.data_ptr(), dst.data_ptr(), int(bool(accumulate)), rows, d, L_in,
-                               src_stride, src_stride if g_stride is None else g_stride, L_out, l_off, _stream()),
-          "tan_l2norm_bwd")
+    with _timed("l2norm_bwd", 0.0):
+        check(lib().tan_l2norm_bwd(x.data_ptr(), g.data_ptr(), dst.data_ptr(), int(bool(accumulate)), rows, d, L_in,
+                                   src_stride, src_stride if g_stride is None else g_stride, L_out, l_off, _stream()),
+              "tan_l2norm_bwd")
     _launches += 1
 
 
@@ -402,8 +409,9 @@ def batch_sum(x: torch.Tensor, out: torch.Tensor, B: int, L: int, d: int, L_out:
     global _launches
     if _skip("bwd_glue", float(B) * L * d):
         return
-    check(lib().tan_batch_sum(x.data_ptr(), out.data_ptr(), B, L, d, L_out, l_off, int(bool(accumulate)), _stream()),
-          "tan_batch_sum")
+    with _timed("batch_sum", 0.0):
+        check(lib().tan_batch_sum(x.data_ptr(), out.data_ptr(), B, L, d, L_out, l_off, int(bool(accumulate)), _stream()),
+              "tan_batch_sum")
     _launches += 1
 
 
@@ -413,10 +421,27 @@ def sim_grad_tiles(z: torch.Tensor, Rc: int, r0: int, g: SimGeom, posbits, col_v
     global _launches
     if _skip("bwd_glue", float(Rc) * g.C):
         return
-    check(lib().tan_sim_grad_tiles(z.data_ptr(), z.stride(0), Rc, pad64(Rc), r0, C.byref(g), posbits.data_ptr(),
-                                   col_valid.data_ptr(), _ptr(row_kill), ra.data_ptr(), rap.data_ptr(), cb.data_ptr(),
-                                   cbp.data_ptr(), G.data_ptr(), G.stride(0), GT.data_ptr(), GT.stride(0), _stream()),
-          "tan_sim_grad_tiles")
+    with _timed("sim_grad", 0.0):
+        check(lib().tan_sim_grad_tiles(z.data_ptr(), z.stride(0), Rc, pad64(Rc), r0, C.byref(g), posbits.data_ptr(),
+                                       col_valid.data_ptr(), _ptr(row_kill), ra.data_ptr(), rap.data_ptr(), cb.data_ptr(),
+                                       cbp.data_ptr(), G.data_ptr(), G.stride(0), GT.data_ptr(), GT.stride(0), _stream()),
+              "tan_sim_grad_tiles")
+    _launches += 1
+
+
+def sim_grad_gemm(a: torch.Tensor, t_pad: torch.Tensor, r0: int, g: SimGeom, posbits, col_valid, row_kill, ra, rap, cb,
+                  cbp, G: torch.Tensor) -> None:
+    """tan_sim_grad_gemm: a [Rc, d] bf16 video rows, t_pad [Cp, d] bf16 text rows (zero beyond C) -> G [Rc, Cp] bf16."""
+    global _launches
+    Rc, d = a.shape
+    Cp = t_pad.shape[0]
+    if _skip("sim_bwd", 2.0 * Rc * Cp * d):
+        return
+    with _timed("sim_bwd", 2.0 * Rc * Cp * d):
+        check(lib().tan_sim_grad_gemm(a.data_ptr(), a.stride(0), t_pad.data_ptr(), t_pad.stride(0), Rc, r0, C.byref(g), Cp,
+                                      posbits.data_ptr(), col_valid.data_ptr(), _ptr(row_kill), ra.data_ptr(),
+                                      rap.data_ptr(), cb.data_ptr(), cbp.data_ptr(), G.data_ptr(), G.stride(0), _stream()),
+              "tan_sim_grad_gemm")
     _launches += 1
 
 

@@ -184,6 +184,22 @@ class TanStepRunner:
             return self._graph_loss
         return self._step_kernels()
 
+    # -- training step: forward with tape + get_loss + backward (no optimizer) -------------------------
+    def step_train(self) -> torch.Tensor:
+        """fwd + loss + bwd on the resident inputs through the public API (model(...), get_loss, loss.backward()):
+        SURVEY.md 8(d) "full train step (fwd+loss+bwd, no optimizer)".  Gradients land in `.grad`."""
+        m = self.model
+        m.train()
+        m.enable_autograd(True)
+        for p in m.parameters():
+            p.grad = None
+        out = m(self.d_video, self.d_text, video_padding_mask=self.d_vpm, lang_padding_mask=self.d_tpm)
+        ld = loss_mod.get_loss(self.input_data, self.d_video, self.d_text, self.d_vpm, self.d_tpm, out, self.args,
+                               None, shard_batch=self.shard)
+        ld["loss"].backward()
+        m.enable_autograd(False)                     # the forward-only steps of this runner stay on the inference path
+        return ld["loss"].detach()
+
     # -- work accounting (SURVEY.md 8(d)) -----------------------------------------------------------
     def flops_per_clip(self, B_glob: Optional[int] = None) -> dict:
         d, T, N, E, D = self.width, self.T, self.N, self.E, self.D

@@ -130,6 +130,11 @@ def test_l2norm_bwd_and_batch_sum():
     dst2 = dst0.clone()
     ops.l2norm_bwd(x.view(-1, d)[s * T:], g.view(-1, d)[s * T:], dst2, True, B * T, d, T, S * T, L, 0)
     assert (dst2.view(B, L, d)[:, :T] - (dst0.view(B, L, d)[:, :T] + xr.grad)).abs().max().item() < 1e-5
+    # gradient stored stage-major ([S, B, T, d]: clip stride T) while x keeps the [B, S, T, d] layout
+    g_sm = g.permute(1, 0, 2, 3).contiguous()
+    dst3 = torch.empty(B * L, d, dtype=torch.float32, device=DEV)
+    ops.l2norm_bwd(x.view(-1, d)[s * T:], g_sm[s].view(-1, d), dst3, False, B * T, d, T, S * T, L, 0, g_stride=T)
+    assert (dst3.view(B, L, d)[:, :T] - xr.grad).abs().max().item() < 1e-5 * max(1.0, xr.grad.abs().max().item())
     # batch sum over the clips of rows [T, T+N) of every clip
     out = torch.ones(N, d, dtype=torch.float32, device=DEV)
     ops.batch_sum(dst0, out, B, N, d, L, T, True)
@@ -190,9 +195,11 @@ def test_attention_bwd(B, H, Lq, Lk, masked):
         assert torch.isfinite(got.float()).all()
 
 
-def test_sim_grad_tiles_and_gemms():
+@pytest.mark.parametrize("with_kill", [False, True])
+def test_sim_grad_tiles_and_gemms(with_kill):
     """dA = G @ B, dB = G^T @ A through tan_sim_grad_tiles + tan_linear_bf16 against autograd of the closed-form
-    MIL-NCE loss (train/loss.py:231-275) on the same bf16 features, one stage."""
+    MIL-NCE loss (train/loss.py:231-275) on the same bf16 features, one stage.  with_kill: some frames lose their
+    own-clip entries (row_kill, the -6e4 fill of padded frames under --learn_agreement)."""
     ops = _ops()
     B, T, N, d = 4, 40, 6, 512
     C = B * N
@@ -222,6 +229,22 @@ def test_sim_grad_tiles_and_gemms():
     pos = pos.to(DEV)
     cv = col_valid.bool()
     zv = z.masked_fill(~cv[None, :], float("-inf"))
+    row_kill = None
+    if with_kill:
+        kill = torch.zeros(B, T, dtype=torch.bool)
+        kill[1, T - 6:] = True
+        kill[2, T - 3:] = True
+        mask = mask & ~kill[:, None, :]                           # killed frames carry no positives
+        posbits = pack_posbits(mask).to(DEV)
+        pos = torch.zeros(R, C, dtype=torch.bool)
+        for b in range(B):
+            pos[b * T:(b + 1) * T, b * N:(b + 1) * N] = mask[b].t()
+        pos = pos.to(DEV)
+        own = torch.zeros(R, C, dtype=torch.bool)
+        for b in range(B):
+            own[b * T:(b + 1) * T, b * N:(b + 1) * N] = True
+        zv = zv.masked_fill((own & kill.view(-1)[:, None]).to(DEV), float("-inf"))
+        row_kill = kill.to(torch.uint8).to(DEV).contiguous()
     row_all = torch.logsumexp(zv, 1)
     row_pos = torch.logsumexp(zv.masked_fill(~pos, float("-inf")), 1)
     rsel = pos.any(1)
@@ -248,9 +271,16 @@ def test_sim_grad_tiles_and_gemms():
     ops.linear(a, tpad, out_f32=zbuf)
     G = torch.empty(R, Cp, dtype=torch.bfloat16, device=DEV)
     GT = torch.empty(C, ops.pad64(R), dtype=torch.bfloat16, device=DEV)
-    ops.sim_grad_tiles(zbuf, R, 0, g, posbits, col_valid, None, ra, rap, cb, cbp, G, GT)
+    ops.sim_grad_tiles(zbuf, R, 0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G, GT)
     assert torch.equal(GT[:, :R], G[:, :C].t())
     assert (GT[:, R:] == 0).all() and (G[:, C:] == 0).all()
+    # the fused variant: G in the epilogue of the recomputation GEMM (no fp32 cosines in HBM)
+    G2 = torch.full((R, Cp), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.sim_grad_gemm(a, tpad, 0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G2)
+    torch.cuda.synchronize()
+    assert (G2[:, C:] == 0).all()
+    assert ((G2.float() - G.float()).norm() / G.float().norm()).item() < 1e-2
+    assert (G2.float() - G.float()).abs().max().item() < 2e-2 * G.float().abs().max().item()
     tT = ops.transpose_bf16(tpad)                               # [d, Cp]
     aT = ops.transpose_bf16(a)                                  # [d, pad64(R)]
     dA = torch.empty(R, d, dtype=torch.float32, device=DEV)

@@ -150,3 +150,52 @@ def test_sgd_step_reduces_loss():
         losses.append(loss.item())
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], losses
+
+
+def test_wgrad_split_over_streams():
+    """Weight gradient with the contraction split into concurrent chunks (train._wgrad) == dy^T @ x."""
+    from temporalalignnet_b200 import train
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 12288 + 100, 512, 1024
+    dy = (torch.randn(M, N, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
+    x = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
+    gw = torch.ones(N, K, dtype=torch.float32, device=DEV)
+    train._wgrad(dy, x, gw)
+    torch.cuda.synchronize()
+    ref = 1.0 + dy.float().t() @ x.float()
+    assert ((gw - ref).norm() / ref.norm()).item() < 1e-4
+    gw2 = torch.ones(N, K, dtype=torch.float32, device=DEV)
+    train._wgrad(dy, x, gw2)
+    torch.cuda.synchronize()
+    assert torch.equal(gw, gw2)                               # fixed-order partial sums: deterministic
+
+
+def test_cotrain_twin_step_runs():
+    """Stage-2 recipe (train/main.py:88-123): online forward with autograd, EMA forward, get_loss(model='cotrain',
+    learn_agreement=1), backward, optimizer step, momentum update."""
+    from temporalalignnet_b200 import TwinTemporalAligner, get_loss
+    cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
+    m = TwinTemporalAligner(m=0.99, num_encoder_layers=1, num_decoder_layers=1, random_pos_start=0).to(DEV)
+    m.online.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    m._copy_param()
+    m.train()
+    m.enable_autograd(True)
+    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.01)
+    video, text = torch.from_numpy(batch["video"]).to(DEV), torch.from_numpy(batch["text"]).to(DEV)
+    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
+    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
+    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    ema = m.forward_from_ema(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    out.update({"ema-" + k: v for k, v in ema.items()})
+    input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
+    res = get_loss(input_data, video, text, vpm.float(), tpm.float(), out, _args(model="cotrain", learn_agreement=1),
+                   None)
+    assert res["loss"].requires_grad and "confidence-ratio" in res
+    w0 = m.target.video_pre_proj.weight.detach().clone()
+    res["loss"].backward()
+    got = [p.grad for p in m.online.parameters() if p.grad is not None]
+    assert len(got) >= 37 and all(torch.isfinite(g).all() for g in got)
+    assert all(p.grad is None for p in m.target.parameters())
+    opt.step()
+    m._momentum_update()
+    assert not torch.equal(w0, m.target.video_pre_proj.weight)
