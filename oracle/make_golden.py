@@ -187,13 +187,14 @@ def run_loss_cases():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "g_loss_full.npz"), **out)
 
 
-# parameter-gradient fixtures (training step): name -> (model case, loss-arg overrides).  The alignability head is
-# switched off (its BCE branch is not differentiated by the CUDA path yet).
+# parameter-gradient fixtures (training step): name -> (model case, loss-arg overrides).  The model carries the
+# alignability head only when the loss uses it (g2_head).
 GRAD_CASES = {
     "g1": ("g1_e1d1_T32_B4", {}),
     "g2": ("g2_e2d3_T24_B3", {}),
     "g2_thr": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5)),
     "g3": ("g3_e6d6_T64_B2", {}),
+    "g2_head": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5, use_alignability_head=1)),
 }
 GRAD_STRIDE = 997        # every 997th element of each parameter gradient is stored (+ its norm)
 
@@ -206,7 +207,7 @@ def run_param_grads():
     out = {}
     for tag, (case, kw) in GRAD_CASES.items():
         cfg = CASES[case]
-        m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], 0)
+        m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], int(kw.get("use_alignability_head", 0)))
         m.train()
         batch = synth.make_batch(cfg["B"], cfg["T"], cfg["N"], pad_video_every=cfg["pad_video_every"])
         video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])

@@ -390,6 +390,7 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     loss_th = None
     loss_bce = None
     row_sel = col_sel = None
+    bce_dx = None
     if thr > 0 or head:
         # ---- keep the most alignable sentences (train/loss.py:277-304) -----------------------------
         if md is None:
@@ -426,6 +427,9 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
             pw = 1.0 / ((y * sel).sum() / n_sel) - 1.0
             sp = torch.nn.functional.softplus
             loss_bce = ((pw * y * sp(-xj) + (1 - y) * sp(xj)) * sel).sum() / n_sel
+            if want_grad:     # d loss_bce / d x of the local sentences (pos_weight and labels carry no gradient)
+                dxj = sel * ((1 - y) * torch.sigmoid(xj) - pw * y * torch.sigmoid(-xj)) / n_sel
+                bce_dx = dxj.view(-1, N)[nce.b_off:nce.b_off + B].contiguous()
             loss_dict['loss-joint-bce'] = loss_bce.detach()
             loss_dict['alignability_top1'] = ((((xj > 0).float() == y).float()) * sel).sum() / n_sel
     nce_weight = 0.0 if getattr(args, "optim_policy", "default") == "bce" else 1.0
@@ -439,6 +443,7 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     if want_grad:
         from . import train
         loss = train.attach_autograd(loss, tape, train.SimCtx(logits_dual, rs_d, cs_d, nce, row_sel, col_sel),
-                                     train.SimCtx(logits_joint, rs_j, cs_j, nce, row_sel, col_sel), nce_weight, dist)
+                                     train.SimCtx(logits_joint, rs_j, cs_j, nce, row_sel, col_sel), nce_weight, dist,
+                                     bce_dx)
     loss_dict['loss'] = loss
     return loss_dict

@@ -13,7 +13,7 @@ libtan_b200.so: every GEMM-shaped gradient (dgrad, wgrad, the similarity recompu
 a `tan_linear_bf16` call on transposed operands (tcgen05 pair GEMM), the rest are the kernels of backward.cu.
 torch only allocates buffers and carries the result into `.grad`.
 
-Not differentiated (raise): the alignability head's BCE branch, `interpolate_from`, sine positions are constants.
+Not differentiated (raise): `interpolate_from` (evaluation-time option); sine positions are constants.
 """
 from __future__ import annotations
 
@@ -135,9 +135,8 @@ def forward_train(model, video_embed, lang_embed, video_padding_mask=None, lang_
     from .tan_model import LazyLogits
     if interpolate_from:
         raise TanError("interpolate_from is an evaluation-time option; the training forward does not support it")
-    if model.use_alignability_head:
-        raise NotImplementedError("the alignability head (BCE branch) is not differentiated yet; "
-                                  "use_alignability_head=1 runs forward-only")
+    if model.use_alignability_head and model.num_decoder_layers < 3:
+        raise TanError("the alignability head reads joint stage 2 (train/loss.py:341): num_decoder_layers >= 3")
     B, T, Din = video_embed.shape
     N = lang_embed.shape[1]
     dev = video_embed.device
@@ -212,6 +211,9 @@ def forward_train(model, video_embed, lang_embed, video_padding_mask=None, lang_
     if model.return_dual_feature:
         out['dual_feature_video'] = vfeat_dual
         out['dual_feature_text'] = tfeat_dual_f32
+    if model.use_alignability_head:      # Linear(d, 1) on the raw text features (model/tan_model.py:146-148): tiny glue
+        out['dual_logits_alignability'] = model._binary_head(tape.text_raw)
+        out['joint_logits_alignability'] = model._binary_head(tape.joint.rawB.permute(1, 0, 2, 3))    # [B,D,N,1]
     return out
 
 
@@ -430,8 +432,9 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
 
 
 def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out: torch.Tensor, nce_weight: float,
-                  dist, params: List[torch.Tensor]) -> List[Optional[torch.Tensor]]:
-    """d (grad_out * nce_weight * (loss_dual + loss_joint) / 2) / d params, in the order of `params`."""
+                  dist, params: List[torch.Tensor], bce_dx: Optional[torch.Tensor] = None) -> List[Optional[torch.Tensor]]:
+    """d (grad_out * (nce_weight * (loss_dual + loss_joint) / 2 + loss_bce)) / d params, in the order of `params`.
+    bce_dx [B_loc, N]: d loss_bce / d joint_logits_alignability[:, 2, :, 0] of the local clips (train/loss.py:341-351)."""
     model = tape.model
     B, T, N = tape.B, tape.T, tape.N
     d, E, D = model.width, model.num_encoder_layers, model.num_decoder_layers
@@ -465,6 +468,15 @@ def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out:
         sg_j.append(buf)
     sg_text = torch.empty(B * N, d, **f32)
     ops.l2norm_bwd(tape.text_raw.view(-1, d), dt_dual[0, own], sg_text, False, B * N, d, N, N, N, 0)
+
+    # ---- alignability head: Linear(d, 1) on the raw joint text features of stage 2 ([B*N]-sized glue) -------
+    if bce_dx is not None:
+        head = model.binary_head
+        gx = (bce_dx.to(torch.float32) * grad_out.detach().to(torch.float32)).reshape(B * N, 1)
+        feat = tape.joint.rawB[2].reshape(B * N, d)
+        grads.of(head.weight).add_((gx * feat).sum(0, keepdim=True))
+        grads.of(head.bias).add_(gx.sum().reshape(1))
+        sg_j[2].view(B, L, d)[:, T:, :].add_((gx * head.weight.detach().float().view(1, d)).view(B, N, d))
 
     # ---- encoder stacks -------------------------------------------------------------------------------
     dx0v = stack_backward(vt, sg_v, grads)                        # [B*T, d]
@@ -541,14 +553,16 @@ class _TanLossFn(torch.autograd.Function):
             raise TanError("this forward's tape was already consumed by a backward pass (retain_graph is not supported)")
         h["tape"].consumed = True
         with torch.no_grad():
-            gs = step_backward(h["tape"], h["dual"], h["joint"], grad_out, h["nce_weight"], h["dist"], h["params"])
+            gs = step_backward(h["tape"], h["dual"], h["joint"], grad_out, h["nce_weight"], h["dist"], h["params"],
+                               h["bce_dx"])
         gs = [None if g is None else g.to(p.dtype) for g, p in zip(gs, h["params"])]
         return (None, None, *gs)
 
 
 def attach_autograd(loss_value: torch.Tensor, tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, nce_weight: float,
-                    dist) -> torch.Tensor:
+                    dist, bce_dx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Wrap the computed loss value into a tensor whose `.backward()` runs the hand-written backward pass."""
     params = [p for p in tape.model.parameters() if p.requires_grad]
-    holder = dict(tape=tape, dual=ctx_dual, joint=ctx_joint, nce_weight=float(nce_weight), dist=dist, params=params)
+    holder = dict(tape=tape, dual=ctx_dual, joint=ctx_joint, nce_weight=float(nce_weight), dist=dist, params=params,
+                  bce_dx=bce_dx)
     return _TanLossFn.apply(loss_value, holder, *params)

@@ -78,15 +78,17 @@ def cpu_pos_from_time(start, end, valid, B, T, N):
 
 
 def oracle_param_grads(cfg, sd, batch, args):
-    """(loss, {name: d loss / d parameter}) by torch autograd over the fp32 CPU oracle (alignability head off)."""
+    """(loss, {name: d loss / d parameter}) by torch autograd over the fp32 CPU oracle.  The alignability head is
+    part of the model only when `args.use_alignability_head` is set."""
     from oracle import tan_oracle as O
-    sd_t = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sd.items() if not k.startswith("binary_head")}
-    orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"])
+    head = int(getattr(args, "use_alignability_head", 0))
+    sd_t = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sd.items()
+            if head or not k.startswith("binary_head")}
+    orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"], use_alignability_head=head)
     orc.sd = sd_t                                                   # keep the leaves (the constructor re-wraps)
     out = orc.forward(batch["video"], batch["text"], batch["video_padding_mask"], batch["text_padding_mask"])
-    if getattr(args, "learn_agreement", 0) or getattr(args, "loss_threshold", 0.0) > 0:
-        res = O.get_loss_full({"logits_dual": out["logits_dual"], "logits_joint": out["logits_joint"]},
-                              batch["start"], batch["end"], torch.from_numpy(batch["video_padding_mask"]),
+    if head or getattr(args, "learn_agreement", 0) or getattr(args, "loss_threshold", 0.0) > 0:
+        res = O.get_loss_full(out, batch["start"], batch["end"], torch.from_numpy(batch["video_padding_mask"]),
                               torch.from_numpy(batch["text_padding_mask"]), args)
     else:
         res = O.get_loss_init(out["logits_dual"], out["logits_joint"], batch["start"], batch["end"],

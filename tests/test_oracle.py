@@ -194,7 +194,8 @@ def test_full_loss_oracle_matches_live_reference(name):
 # training step: the oracle's parameter gradients (torch autograd over the restatement) against the reference's
 # ------------------------------------------------------------------------------------------------
 GRAD_CASES = {"g1": ("g1_e1d1_T32_B4", {}), "g2": ("g2_e2d3_T24_B3", {}),
-              "g2_thr": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5)), "g3": ("g3_e6d6_T64_B2", {})}
+              "g2_thr": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5)), "g3": ("g3_e6d6_T64_B2", {}),
+              "g2_head": ("g2_e2d3_T24_B3", dict(loss_threshold=0.5, use_alignability_head=1))}
 
 
 @pytest.mark.parametrize("tag", list(GRAD_CASES))
@@ -209,16 +210,16 @@ def test_oracle_param_grads_vs_reference_fixture(tag):
     a = dict(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep", loss_threshold=0.0,
              use_alignability_head=0, optim_policy="default")
     a.update(kw)
-    loss, grads = oracle_param_grads(dict(cfg, head=0), sd, batch, types.SimpleNamespace(**a))
+    loss, grads = oracle_param_grads(cfg, sd, batch, types.SimpleNamespace(**a))
     assert abs(loss - float(g[f"{tag}/loss"])) < 1e-5 * abs(loss)
     names = [k[len(tag) + 6:] for k in g if k.startswith(f"{tag}/norm/")]
     assert len(names) >= 37
     for name in names:
         got = grads[name].double().reshape(-1)
         ref_norm = float(g[f"{tag}/norm/{name}"])
-        assert abs(float(got.norm()) - ref_norm) <= 2e-4 * ref_norm + 1e-9, name
+        assert abs(float(got.norm()) - ref_norm) <= 2e-4 * ref_norm + 5e-7, name      # (floor: cancelling fp32 sums)
         sub = torch.from_numpy(g[f"{tag}/sub/{name}"]).double()
-        assert float((got[::997] - sub).abs().max()) <= 2e-4 * max(float(sub.abs().max()), ref_norm * 1e-2) + 1e-9, name
+        assert float((got[::997] - sub).abs().max()) <= 2e-4 * max(float(sub.abs().max()), ref_norm * 1e-2) + 5e-7, name
     # parameters the reference leaves without gradient get none / zero here as well
     for name, gr in grads.items():
         if name not in names:

@@ -21,12 +21,12 @@ def _args(**kw):
     return types.SimpleNamespace(**d)
 
 
-def _build(cfg, sd):
+def _build(cfg, sd, head=0):
     from temporalalignnet_b200 import TemporalAligner
     m = TemporalAligner(num_encoder_layers=cfg["E"], num_decoder_layers=cfg["D"], sim="cos", language_model="word2vec",
                         pos_enc="learned", use_text_pos_enc=cfg["use_text_pos_enc"], return_dual_feature=1,
-                        random_pos_start=0, use_alignability_head=0)
-    sd = {k: torch.from_numpy(v) for k, v in sd.items() if not k.startswith("binary_head")}
+                        random_pos_start=0, use_alignability_head=head)
+    sd = {k: torch.from_numpy(v) for k, v in sd.items() if head or not k.startswith("binary_head")}
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not missing and not unexpected, (missing, unexpected)
     return m.to(DEV)
@@ -46,6 +46,10 @@ def _compare(model, ref_grads, loose=False):
         assert p.grad is not None, f"no gradient for {name}"
         g = p.grad.detach().float().cpu().double().reshape(-1)
         r = ref.double().reshape(-1)
+        if r.numel() == 1:            # a scalar (binary_head.bias) is a cancelling sum: absolute tolerance
+            if abs(float(g) - float(r)) > 2e-3:
+                bad.append((name, float(g), float(r)))
+            continue
         cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-300))
         rel = float((g - r).norm() / r.norm())
         small = p.dim() == 1
@@ -199,3 +203,25 @@ def test_cotrain_twin_step_runs():
     opt.step()
     m._momentum_update()
     assert not torch.equal(w0, m.target.video_pre_proj.weight)
+
+
+def test_backward_with_alignability_head_vs_oracle_autograd():
+    """BASELINE config 5's loss recipe at toy size: thresholded NCE + BCE of the alignability head on joint stage 2
+    (train/loss.py:306-357): gradients reach binary_head and, through it, the joint stack."""
+    from temporalalignnet_b200 import get_loss
+    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
+    args = _args(loss_threshold=0.5, use_alignability_head=1)
+    ref_loss, ref_grads = _oracle_grads(cfg, sd, batch, args)
+    m = _build(cfg, sd, head=1)
+    m.enable_autograd(True)
+    video, text = torch.from_numpy(batch["video"]).to(DEV), torch.from_numpy(batch["text"]).to(DEV)
+    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
+    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
+    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
+    res = get_loss(input_data, video, text, vpm.float(), tpm.float(), out, args, None)
+    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss), (res["loss"].item(), ref_loss)
+    res["loss"].backward()
+    torch.cuda.synchronize()
+    assert m.binary_head.weight.grad is not None and m.binary_head.bias.grad is not None
+    _compare(m, ref_grads, loose=True)
