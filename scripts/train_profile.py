@@ -16,16 +16,18 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 r = TanStepRunner(6, 6, B_loc=B, T=T, use_graph=False)
-for _ in range(2):
+for _ in range(2 if steps > 0 else 1):          # steps == 0: one warm-up + the profiled step (ncu launch lists)
     loss = r.step_train()
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(steps):
-    loss = r.step_train()
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / steps
+ms = float("nan")
+if steps > 0:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = r.step_train()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
 n0 = ops.launches()
 with ops.profile() as prof:
     r.step_train()
