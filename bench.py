@@ -351,7 +351,7 @@ def train_step_leg(runner, steps, flush, fl, tf_peak):
         tf = 3.0 * fl["total"] * runner.B / (ms * 1e-3) / 1e12
         return {"value": round(runner.B / (ms * 1e-3), 1), "unit": "clips/s", "ms_per_step": round(ms, 3),
                 "steps": steps, "what": "forward (activations kept) + get_loss + loss.backward(), no optimizer; eager "
-                "launches; first correct backward path (DESIGN.md section 8)", "loss": round(float(loss), 6),
+                "launches; first correct backward path (DESIGN.md section 7)", "loss": round(float(loss), 6),
                 "grad_norm": round(gn, 6), "achieved": round(tf, 1), "peak": tf_peak, "unit_flops": "TFLOP/s",
                 "frac": round(tf / tf_peak, 4), "max_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
     except Exception as e:                                   # never lose the headline line to the extra leg
