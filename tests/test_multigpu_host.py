@@ -81,13 +81,68 @@ def _worker(rank, world, port, ret):
                                pos_fn=cpu_pos_from_time)
     assert nce.b_off == rank * B_loc and nce.B_glob == Bg and nce.col_valid.numel() == Bg * N
     assert tuple(nce.posbits.shape) == (B_loc, T, 1)
-    losses = []
+    losses, sums = [], []
     for vfeat, tfeat, shared, S in ((vn, tn, True, E), (jvn, jtn, False, D)):
         tg = L.gather_text_features(tfeat.contiguous(), shared, dist)
         tg3 = tg[None].expand(S, -1, -1) if shared else tg
         row, col = _exp_sums(vfeat, tg3, nce, B_loc, S, T, N)
-        losses.append(L.finish_loss(row, col.contiguous(), dist, T, reduce_fn=_cpu_reduce))
+        col = col.contiguous()
+        losses.append(L.finish_loss(row, col, dist, T, reduce_fn=_cpu_reduce))      # all-reduces `col` in place
+        sums.append((row, col))
     loss = float((losses[0] + losses[1]) / 2)
+    # ---- backward exchange (train.sim_coefficients + the all-reduce rule of train.step_backward) ----------------
+    # The similarity-gradient kernels are replaced by their torch formula; the coefficient vectors, the stage-major
+    # row layout, b_off and the sum of the text-feature gradients over ranks are the product's own host logic.
+    from temporalalignnet_b200 import train as TR
+    scale = torch.tensor(0.5)
+    grad_err = 0.0
+    for vfeat, tfeat, shared, S, (row, col) in ((vn, tn, True, E, sums[0]), (jvn, jtn, False, D, sums[1])):
+        tg = L.gather_text_features(tfeat.contiguous(), shared, dist)
+        tg3 = (tg[None].expand(S, -1, -1) if shared else tg).contiguous()
+        C = tg3.shape[1]
+        lg = type("LG", (), {})()
+        lg.vfeat, lg.tfeat, lg.shared_text = vfeat, tfeat, shared
+        ra, rap, cb, cbp = TR.sim_coefficients(TR.SimCtx(lg, row, col, nce), scale, dist)
+        assert tuple(ra.shape) == (S, B_loc * T) and tuple(cb.shape) == (S, C)
+        valid = nce.col_valid.bool()
+        pos_own = unpack_posbits(nce.posbits, N).permute(0, 2, 1)
+        pos = torch.zeros(B_loc * T, C)
+        for b in range(B_loc):
+            pos[b * T:(b + 1) * T, (nce.b_off + b) * N:(nce.b_off + b + 1) * N] = pos_own[b].float()
+        d_v = torch.zeros(S, B_loc * T, vfeat.shape[-1])
+        d_t = torch.zeros(S, C, vfeat.shape[-1])
+        for s_ in range(S):
+            a = vfeat[:, s_].reshape(B_loc * T, -1)
+            e = torch.exp((a @ tg3[s_].t() - 1.0) / 0.07) * valid.float()[None]
+            G = e * (ra[s_][:, None] + cb[s_][None] - pos * (rap[s_][:, None] + cbp[s_][None])) / 0.07
+            d_v[s_] = G @ tg3[s_]
+            d_t[s_] = G.t() @ a
+        dist.all_reduce(d_t)                                    # text-feature gradients: sum over the ranks' rows
+        if shared:
+            d_t = d_t.sum(0, keepdim=True)
+        # reference: autograd of the oracle's NCE on the GLOBAL batch
+        vg = [torch.zeros_like(vfeat) for _ in range(world)]
+        dist.all_gather(vg, vfeat.contiguous())
+        vg = torch.cat(vg).clone().requires_grad_(True)
+        tref = (tg.clone() if shared else tg3.clone()).requires_grad_(True)
+        mask_g, _, _ = O.mask_from_time(full["start"], full["end"], T, N)
+        tpm_g = torch.from_numpy(full["text_padding_mask"])
+        tgt = torch.zeros(Bg, T, Bg, N, dtype=torch.bool)
+        for b in range(Bg):
+            tgt[b, :, b, :] = mask_g[b].t()
+        cv = (~tpm_g).reshape(-1)
+        tgt = tgt.reshape(Bg * T, Bg * N) & cv[None]
+        logits = (torch.einsum("astc,kc->astk", vg, tref) if shared else
+                  torch.einsum("astc,skc->astk", vg, tref)).reshape(Bg, S, T, Bg, N)
+        (0.5 * O.nce_loss(logits, tgt, cv)).backward()
+        ref_v = vg.grad[sl].permute(1, 0, 2, 3).reshape(S, B_loc * T, -1)
+        ref_t = tref.grad[None] if shared else tref.grad
+        grad_err = max(grad_err, float((d_v - ref_v).abs().max() / ref_v.abs().max()),
+                       float((d_t - ref_t).abs().max() / ref_t.abs().max()))
+    errs = [None] * world
+    dist.all_gather_object(errs, grad_err)
+    if rank == 0:
+        ret["grad_err"] = max(errs)
     if rank == 0:
         ref_out = orc.forward(torch.from_numpy(full["video"]), torch.from_numpy(full["text"]),
                               full["video_padding_mask"], full["text_padding_mask"])
@@ -108,6 +163,8 @@ def test_two_rank_sharded_loss_equals_single_process_oracle():
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert abs(ret["loss"] - ret["ref"]) < 1e-5 * abs(ret["ref"]), (ret["loss"], ret["ref"])
     assert all(abs(x - ret["loss"]) < 1e-7 for x in ret["all"])      # every rank returns the global loss
+    # sharded feature gradients (coefficients + exchange rule of the backward pass) == autograd on the global batch
+    assert ret["grad_err"] < 1e-4, ret["grad_err"]
 
 
 def test_prepare_nce_inputs_single_process_layout():
