@@ -77,16 +77,18 @@ def cpu_pos_from_time(start, end, valid, B, T, N):
     return pack_posbits(m)
 
 
-def oracle_param_grads(cfg, sd, batch, args):
+def oracle_param_grads(cfg, sd, batch, args, pos_starts=(0, 0, 0)):
     """(loss, {name: d loss / d parameter}) by torch autograd over the fp32 CPU oracle.  The alignability head is
-    part of the model only when `args.use_alignability_head` is set."""
+    part of the model only when `args.use_alignability_head` is set.  pos_starts: the three positional-table
+    offsets of a `random_pos_start=1` forward (video stack, text, joint stack)."""
     from oracle import tan_oracle as O
     head = int(getattr(args, "use_alignability_head", 0))
     sd_t = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sd.items()
             if head or not k.startswith("binary_head")}
     orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"], use_alignability_head=head)
     orc.sd = sd_t                                                   # keep the leaves (the constructor re-wraps)
-    out = orc.forward(batch["video"], batch["text"], batch["video_padding_mask"], batch["text_padding_mask"])
+    out = orc.forward(batch["video"], batch["text"], batch["video_padding_mask"], batch["text_padding_mask"],
+                      pos_starts=pos_starts)
     if head or getattr(args, "learn_agreement", 0) or getattr(args, "loss_threshold", 0.0) > 0:
         res = O.get_loss_full(out, batch["start"], batch["end"], torch.from_numpy(batch["video_padding_mask"]),
                               torch.from_numpy(batch["text_padding_mask"]), args)
@@ -95,3 +97,29 @@ def oracle_param_grads(cfg, sd, batch, args):
                               batch["text_padding_mask"])
     res["loss"].backward()
     return float(res["loss"].detach()), {k: v.grad for k, v in sd_t.items()}
+
+
+def compare_param_grads(model, ref_grads, loose=False):
+    """Per parameter: cosine >= 0.999 and rel-Frobenius <= 2e-2 (matrices) / 5e-2 (vectors) against `ref_grads`
+    (SURVEY.md 8(c) tolerances of the bf16 path); `loose` doubles them (thresholded recipes)."""
+    bad = []
+    for name, p in model.named_parameters():
+        ref = ref_grads.get(name)
+        if ref is None or float(ref.norm()) == 0.0:
+            assert p.grad is None or float(p.grad.norm()) == 0.0, name
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        g = p.grad.detach().float().cpu().double().reshape(-1)
+        r = ref.double().reshape(-1)
+        if r.numel() == 1:            # a scalar (binary_head.bias) is a cancelling sum: absolute tolerance
+            if abs(float(g) - float(r)) > 2e-3:
+                bad.append((name, float(g), float(r)))
+            continue
+        cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-300))
+        rel = float((g - r).norm() / r.norm())
+        small = p.dim() == 1
+        tol_rel = (5e-2 if small else 2e-2) * (2.0 if loose else 1.0)
+        tol_cos = 0.998 if (small or loose) else 0.999
+        if not (cos >= tol_cos and rel <= tol_rel):
+            bad.append((name, round(cos, 5), round(rel, 4)))
+    assert not bad, bad

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import CASES, case_inputs, oracle_param_grads
+from tests.helpers import CASES, case_inputs, compare_param_grads, oracle_param_grads
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -37,27 +37,7 @@ def _oracle_grads(cfg, sd, batch, args):
 
 
 def _compare(model, ref_grads, loose=False):
-    bad = []
-    for name, p in model.named_parameters():
-        ref = ref_grads.get(name)
-        if ref is None or float(ref.norm()) == 0.0:
-            assert p.grad is None or float(p.grad.norm()) == 0.0, name
-            continue
-        assert p.grad is not None, f"no gradient for {name}"
-        g = p.grad.detach().float().cpu().double().reshape(-1)
-        r = ref.double().reshape(-1)
-        if r.numel() == 1:            # a scalar (binary_head.bias) is a cancelling sum: absolute tolerance
-            if abs(float(g) - float(r)) > 2e-3:
-                bad.append((name, float(g), float(r)))
-            continue
-        cos = float((g @ r) / (g.norm() * r.norm()).clamp_min(1e-300))
-        rel = float((g - r).norm() / r.norm())
-        small = p.dim() == 1
-        tol_rel = (5e-2 if small else 2e-2) * (2.0 if loose else 1.0)
-        tol_cos = 0.998 if (small or loose) else 0.999
-        if not (cos >= tol_cos and rel <= tol_rel):
-            bad.append((name, round(cos, 5), round(rel, 4)))
-    assert not bad, bad
+    compare_param_grads(model, ref_grads, loose)
 
 
 @pytest.mark.parametrize("name,head_off", [("g1_e1d1_T32_B4", False), ("g2_e2d3_T24_B3", True), ("g3_e6d6_T64_B2", False)])

@@ -1,0 +1,122 @@
+"""Host logic of the training step on CPU (`-m "not gpu"`): `train.forward_train` / `train.step_backward` /
+`get_loss` run with the C-ABI wrappers replaced by torch stand-ins (tests/cpu_ops.py), so what is tested is the
+product's own orchestration -- kernel sequence, saved-activation bookkeeping, stage-gradient injection, row maps of
+the video|text concatenation, positional-table slices, the single autograd node -- against torch autograd over the
+oracle.  The kernels themselves are tested on the GPU (tests/test_backward_kernels_gpu.py, tests/test_train_gpu.py)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from tests import cpu_ops
+from tests.helpers import case_inputs, compare_param_grads, oracle_param_grads
+
+
+def _args(**kw):
+    d = dict(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep", loss_threshold=0.0,
+             use_alignability_head=0, optim_policy="default")
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def _model(cfg, sd, head=0, **kw):
+    from temporalalignnet_b200 import TemporalAligner
+    m = TemporalAligner(num_encoder_layers=cfg["E"], num_decoder_layers=cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"],
+                        use_alignability_head=head, **kw)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items() if head or not k.startswith("binary_head")})
+    m.train()
+    m.enable_autograd(True)
+    return m
+
+
+def _step(m, batch, args):
+    from temporalalignnet_b200 import get_loss
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    res = get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}, video, text,
+                   vpm.float(), tpm.float(), out, args, None, shard_batch=False)
+    res["loss"].backward()
+    return out, res
+
+
+@pytest.mark.parametrize("name,kw,head", [("g1_e1d1_T32_B4", {}, 0), ("g2_e2d3_T24_B3", {}, 0),
+                                          ("g2_e2d3_T24_B3", dict(loss_threshold=0.5, use_alignability_head=1), 1)])
+def test_training_step_host_logic_vs_oracle_autograd(monkeypatch, name, kw, head):
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs(name)
+    args = _args(**kw)
+    ref_loss, ref_grads = oracle_param_grads(dict(cfg, head=head), sd, batch, args)
+    m = _model(cfg, sd, head=head, random_pos_start=0)
+    _, res = _step(m, batch, args)
+    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss), (res["loss"].item(), ref_loss)
+    compare_param_grads(m, ref_grads, loose=bool(kw))
+    assert m.mlp.weight.grad is None
+
+
+def test_random_pos_start_offsets_reach_the_right_table_rows(monkeypatch):
+    """random_pos_start=1 (the reference's training default, model/tan_model.py:162-165,:195,:224): three draws from
+    the global numpy RNG pick the table slices of the video stack, the text positions and the joint stack; the
+    gradient of each slice must land in exactly those rows of temporal_pos_embed / text_temporal_pos_embed."""
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
+    m = _model(cfg, sd, random_pos_start=1)
+    np.random.seed(7)
+    out, res = _step(m, batch, _args())
+    tape = out["logits_dual"].tape
+    starts = (tape.ps_v, tape.ps_t, tape.ps_j)
+    assert tape.ps_v != tape.ps_j, "pick a seed whose two video draws differ (exercises the two-slice path)"
+    ref_loss, ref_grads = oracle_param_grads(dict(cfg, head=0), sd, batch, _args(), pos_starts=starts)
+    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss)
+    compare_param_grads(m, ref_grads)
+    T = cfg["T"]
+    g = m.temporal_pos_embed.grad
+    used = torch.zeros(g.shape[0], dtype=torch.bool)
+    used[tape.ps_v:tape.ps_v + T] = True
+    used[tape.ps_j:tape.ps_j + T] = True
+    assert float(g[~used].abs().max()) == 0.0 and float(g[used].abs().min(dim=1).values.min()) >= 0.0
+    assert float(g[used].abs().sum(dim=1).min()) > 0.0
+
+
+def test_sine_positions_are_constants(monkeypatch):
+    """pos_enc='sine': the table is a buffer (model/tan_model.py:60-62); only ln_position_init learns."""
+    from temporalalignnet_b200.tfm_model import get_position_embedding_sine
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
+    sd = dict(sd)
+    sd["temporal_pos_embed"] = get_position_embedding_sine(512, 1024).numpy().astype(np.float32)
+    ref_loss, ref_grads = oracle_param_grads(dict(cfg, head=0), sd, batch, _args())
+    ref_grads.pop("temporal_pos_embed")
+    m = _model(cfg, sd, random_pos_start=0, pos_enc="sine")
+    assert "temporal_pos_embed" not in dict(m.named_parameters())
+    _, res = _step(m, batch, _args())
+    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss)
+    compare_param_grads(m, ref_grads)
+    assert m.ln_position_init.weight.grad is not None
+
+
+def test_inference_paths_carry_no_tape(monkeypatch):
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
+    m = _model(cfg, sd, random_pos_start=0)
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    m.two_streams = False
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: None)
+    with torch.no_grad():
+        out = m(video, text)
+    assert getattr(out["logits_dual"], "tape", None) is None
+    m.eval()
+    assert getattr(m(video, text)["logits_dual"], "tape", None) is None
+    m.train()
+    assert getattr(m(video, text)["logits_dual"], "tape", None) is not None
+
+
+def test_second_backward_on_a_consumed_tape_raises(monkeypatch):
+    from temporalalignnet_b200 import TanError
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
+    m = _model(cfg, sd, random_pos_start=0)
+    _, res = _step(m, batch, _args())
+    with pytest.raises((TanError, RuntimeError)):
+        res["loss"].backward()
