@@ -75,7 +75,23 @@ def cpu_reference_clips_per_sec(steps, warmup, clips=CPU_SAMPLE_CLIPS):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
+
+    # the same sample as a full training step (fwd + loss + bwd through torch autograd, no optimizer): the CPU
+    # counterpart of the GPU arm's `train_step` leg (SURVEY.md 8(d) asks for both); 1 warm-up + best of 2
+    def train_step_cpu():
+        leaves = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in sd.items()}
+        orc.sd = leaves
+        out = orc.forward(video, text, batch["video_padding_mask"], batch["text_padding_mask"])
+        O.get_loss_init(out["logits_dual"], out["logits_joint"], batch["start"], batch["end"],
+                        batch["text_padding_mask"])["loss"].backward()
+    train_times = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        train_step_cpu()
+        if i > 0:
+            train_times.append(time.perf_counter() - t0)
     return {"value": clips / (sum(times) / len(times)), "best": clips / min(times), "cores": cores,
+            "train_value": clips / min(train_times),
             "sample": f"{clips} clips (E6D6, T={T_FRAMES}, N={N_TEXT}; negatives span only the {clips}-clip sample, "
                       f"i.e. 1/{B_GLOBAL // clips} of the workload's similarity work per clip -- the reference's fp32 "
                       f"logits of the full batch, 2 x 12.9 GB, do not fit the time budget), "
@@ -93,7 +109,7 @@ def run_reference_arm(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": round(r["value"], 3), "unit": "clips/s", "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"]},
+                             "sample": r["sample"], "train_step_value": round(r["train_value"], 3)},
             "e2e": {"value": round(r["value"], 3), "unit": "clips/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -308,7 +324,8 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         r = cpu_reference_clips_per_sec(3, 1)
         cpu = {"value": round(r["best"], 3), "unit": "clips/s", "cores": r["cores"], "kind": "port",
-               "sample": r["sample"].replace("mean of 3", "best of 3")}
+               "sample": r["sample"].replace("mean of 3", "best of 3"),
+               "train_step_value": round(r["train_value"], 3)}      # fwd + loss + bwd (torch autograd) on the same sample
 
     if world > 1:
         dist.barrier()

@@ -4,7 +4,8 @@ sm_100a kernels.  Drop-in surface = the SUPERSET that train/main.py actually cal
 interpolate_from=)`, `lang_model` as well as `bert`, `get_alignability(..., abs_text_pos)`.
 
 Differences from the reference that are part of the design:
-  * forward-only (no autograd graph); bf16 tensor-core math with fp32 accumulation / residuals;
+  * bf16 tensor-core math with fp32 accumulation / residuals; inference calls carry no autograd graph, training
+    goes through `enable_autograd()` (train.py: taped forward + hand-written backward behind one autograd node);
   * the video pre-projection + LayerNorm is computed ONCE per forward (the reference computes it
     twice, model/tan_model.py:155 and :187);
   * `logits_dual` / `logits_joint` are `LazyLogits` handles by default (fused mode): the

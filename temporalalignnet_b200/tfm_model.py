@@ -5,7 +5,8 @@ libtan_b200.so.
 The nn.Module tree (nn.MultiheadAttention / nn.LayerNorm / nn.Linear) is used purely as a parameter
 container so that `state_dict()` keys and shapes equal the reference's
 (`resblocks.{i}.attn.in_proj_weight`, `...mlp.c_fc.weight`, ...); their torch `forward`s are never
-called.  Forward-only (inference / loss evaluation): outputs carry no autograd graph.
+called.  The standalone TemporalEncoder / TemporalDecoder modules are inference-only (outputs carry no autograd
+graph); inside TemporalAligner the stacks are trained through train.py (taped forward + hand-written backward).
 """
 from __future__ import annotations
 
