@@ -58,6 +58,13 @@ class StepTape:
         self.joint = None         # StackTape
         self.consumed = False
 
+    def release(self) -> None:
+        """Drop the saved activations (15 GB at the bench shape) as soon as the backward pass has used them: the
+        loss tensor -- and with it this tape -- usually stays referenced until the next step's loss replaces it."""
+        self.video = self.joint = None
+        for name in ("vb", "tb", "pre_v", "pre_t", "text_raw"):
+            setattr(self, name, None)
+
 
 def run_encoder_stack_train(enc, x0: torch.Tensor, kpm, B: int, L: int, l_split: int, post_ln,
                             nrm_sink: StageSink) -> StackTape:
@@ -555,6 +562,8 @@ class _TanLossFn(torch.autograd.Function):
         with torch.no_grad():
             gs = step_backward(h["tape"], h["dual"], h["joint"], grad_out, h["nce_weight"], h["dist"], h["params"],
                                h["bce_dx"])
+        h["tape"].release()
+        h["dual"] = h["joint"] = None                 # the features / exp-sums of the step
         gs = [None if g is None else g.to(p.dtype) for g, p in zip(gs, h["params"])]
         return (None, None, *gs)
 
