@@ -575,3 +575,19 @@ def attach_autograd(loss_value: torch.Tensor, tape: StepTape, ctx_dual: SimCtx, 
     holder = dict(tape=tape, dual=ctx_dual, joint=ctx_joint, nce_weight=float(nce_weight), dist=dist, params=params,
                   bce_dx=bce_dx)
     return _TanLossFn.apply(loss_value, holder, *params)
+
+
+@torch.no_grad()
+def clip_gradients(model, clip_grad=3, return_norms: bool = True):
+    """utils/train_utils.py:3-13 (per-parameter L2 clipping, called at train/main.py:115-116) without its one
+    `.item()` host synchronisation PER PARAMETER (~160 per step): multi-tensor norms, one clamped coefficient
+    vector, one multi-tensor scale.  Same arithmetic as the reference (coefficients >= 1 leave the gradient
+    untouched bit for bit).  Returns the list of norms like the reference (one synchronisation), or the device
+    vector with return_norms=False (none)."""
+    grads = [p.grad for _, p in model.named_parameters() if p.grad is not None]
+    if not grads:
+        return []
+    norms = torch.stack(torch._foreach_norm(grads, 2))
+    coef = (clip_grad / (norms + 1e-6)).clamp(max=1.0)
+    torch._foreach_mul_(grads, list(coef.unbind()))
+    return norms.tolist() if return_norms else norms

@@ -120,3 +120,49 @@ def test_second_backward_on_a_consumed_tape_raises(monkeypatch):
     _, res = _step(m, batch, _args())
     with pytest.raises((TanError, RuntimeError)):
         res["loss"].backward()
+
+
+def test_clip_gradients_matches_reference():
+    """train.clip_gradients == utils/train_utils.py:3-13 (the reference's own function when it is present)."""
+    import os
+    import sys
+
+    from temporalalignnet_b200.train import clip_gradients
+
+    def ref_clip(model, clip_grad=3):                       # restatement of utils/train_utils.py:3-13
+        norms = []
+        for _, p in model.named_parameters():
+            if p.grad is not None:
+                param_norm = p.grad.data.norm(2)
+                norms.append(param_norm.item())
+                clip_coef = clip_grad / (param_norm + 1e-6)
+                if clip_coef < 1:
+                    p.grad.data.mul_(clip_coef)
+        return norms
+
+    if os.path.isfile("/root/reference/utils/train_utils.py"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ref_train_utils", "/root/reference/utils/train_utils.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            ref_clip = mod.clip_gradients
+        finally:
+            sys.path.pop(0)
+    torch.manual_seed(0)
+    a = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    b = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+    b.load_state_dict(a.state_dict())
+    for m in (a, b):
+        for i, p in enumerate(m.parameters()):
+            g = torch.Generator().manual_seed(i)
+            p.grad = torch.randn(p.shape, generator=g) * (10.0 if i % 2 == 0 else 0.01)   # some clipped, some not
+        list(m.parameters())[3].grad = None                                              # and one without gradient
+    n_ref = ref_clip(a, 3)
+    n_got = clip_gradients(b, 3)
+    assert len(n_ref) == len(n_got) and all(abs(x - y) <= 1e-6 * max(1.0, abs(x)) for x, y in zip(n_ref, n_got))
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert (pa.grad is None) == (pb.grad is None)
+        if pa.grad is not None:
+            assert torch.equal(pa.grad, pb.grad)
