@@ -292,3 +292,14 @@ def install(monkeypatch):
     for n in NAMES:
         monkeypatch.setattr(ops, n, getattr(me, n))
     monkeypatch.setattr(tan_model.TemporalAligner, "_check_device", lambda self, t: None)
+
+
+def install_plain():
+    """The same swap without pytest's monkeypatch (spawned worker processes of the gloo tests)."""
+    import sys
+
+    from temporalalignnet_b200 import ops, tan_model
+    me = sys.modules[__name__]
+    for n in NAMES:
+        setattr(ops, n, getattr(me, n))
+    tan_model.TemporalAligner._check_device = lambda self, t: None
