@@ -62,6 +62,7 @@ class StepTape:
         """Drop the saved activations (15 GB at the bench shape) as soon as the backward pass has used them: the
         loss tensor -- and with it this tape -- usually stays referenced until the next step's loss replaces it."""
         self.video = self.joint = None
+        self.input_leaves = []
         for name in ("vb", "tb", "pre_v", "pre_t", "text_raw"):
             setattr(self, name, None)
 
@@ -153,6 +154,10 @@ def forward_train(model, video_embed, lang_embed, video_padding_mask=None, lang_
     kpm_t = _mask_u8(lang_padding_mask, B, N, dev)
     tape = StepTape(model)
     tape.B, tape.T, tape.N, tape.Din, tape.Dt = B, T, N, Din, lang_embed.shape[2]
+    # inputs that take part in autograd (the text backbone's fc1 / fc2 train through `lang_embed` in the reference,
+    # train/main.py:58-60): they become inputs of the step's autograd node next to the parameters
+    tape.input_leaves = [t_ for t_ in (lang_embed, video_embed) if t_.requires_grad]
+    tape.want_text_grad, tape.want_video_grad = bool(lang_embed.requires_grad), bool(video_embed.requires_grad)
     f32 = dict(dtype=torch.float32, device=dev)
     bf = dict(dtype=torch.bfloat16, device=dev)
 
@@ -528,8 +533,19 @@ def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out:
         ops.batch_sum(dx0j, dpos_t, B, N, d, L, T, False)
         pos_backward(model.text_temporal_pos_embed, tape.ps_t, dpos_t, N)
 
-    _wgrad(ops.cast_bf16(dpre_v), tape.vb, grads.of(model.video_pre_proj.weight))
-    _wgrad(ops.cast_bf16(dpre_t), tape.tb, grads.of(model.text_pre_proj.weight))
+    dpre_v_bf, dpre_t_bf = ops.cast_bf16(dpre_v), ops.cast_bf16(dpre_t)
+    _wgrad(dpre_v_bf, tape.vb, grads.of(model.video_pre_proj.weight))
+    _wgrad(dpre_t_bf, tape.tb, grads.of(model.text_pre_proj.weight))
+    # gradients of the inputs that asked for one (dgrad of the bias-free pre-projections)
+    tape.input_grads = []
+    if tape.want_text_grad:
+        d_text = torch.empty(B * N, tape.Dt, **f32)
+        _dgrad(dpre_t_bf, ops.transpose_bf16(model._cache.get(model.text_pre_proj.weight)), out_f32=d_text)
+        tape.input_grads.append(d_text.view(B, N, tape.Dt))
+    if tape.want_video_grad:
+        d_video = torch.empty(B * T, tape.Din, **f32)
+        _dgrad(dpre_v_bf, ops.transpose_bf16(model._cache.get(model.video_pre_proj.weight)), out_f32=d_video)
+        tape.input_grads.append(d_video.view(B, T, tape.Din))
 
     out = [grads.get(p) for p in params]
     if dist is not None:                                           # weights are replicated: sum the ranks' gradients
@@ -548,9 +564,9 @@ class _TanLossFn(torch.autograd.Function):
     backward runs `step_backward` and hands every parameter its gradient."""
 
     @staticmethod
-    def forward(ctx, loss_value, holder, *params):
+    def forward(ctx, loss_value, holder, *inputs):          # inputs = parameters + input tensors that require grad
         ctx.holder = holder
-        ctx.n = len(params)
+        ctx.n = len(inputs)
         return loss_value.detach().clone()
 
     @staticmethod
@@ -562,10 +578,11 @@ class _TanLossFn(torch.autograd.Function):
         with torch.no_grad():
             gs = step_backward(h["tape"], h["dual"], h["joint"], grad_out, h["nce_weight"], h["dist"], h["params"],
                                h["bce_dx"])
+        in_grads = [g.to(t_.dtype) for g, t_ in zip(h["tape"].input_grads, h["tape"].input_leaves)]
         h["tape"].release()
         h["dual"] = h["joint"] = None                 # the features / exp-sums of the step
         gs = [None if g is None else g.to(p.dtype) for g, p in zip(gs, h["params"])]
-        return (None, None, *gs)
+        return (None, None, *gs, *in_grads)
 
 
 def attach_autograd(loss_value: torch.Tensor, tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, nce_weight: float,
@@ -574,7 +591,7 @@ def attach_autograd(loss_value: torch.Tensor, tape: StepTape, ctx_dual: SimCtx, 
     params = [p for p in tape.model.parameters() if p.requires_grad]
     holder = dict(tape=tape, dual=ctx_dual, joint=ctx_joint, nce_weight=float(nce_weight), dist=dist, params=params,
                   bce_dx=bce_dx)
-    return _TanLossFn.apply(loss_value, holder, *params)
+    return _TanLossFn.apply(loss_value, holder, *params, *tape.input_leaves)
 
 
 @torch.no_grad()

@@ -205,3 +205,39 @@ def test_backward_with_alignability_head_vs_oracle_autograd():
     torch.cuda.synchronize()
     assert m.binary_head.weight.grad is not None and m.binary_head.bias.grad is not None
     _compare(m, ref_grads, loose=True)
+
+
+def test_gradients_reach_the_text_and_video_inputs():
+    """`lang_embed` / `video_embed` that require grad (the reference trains the text backbone through lang_embed,
+    train/main.py:58-60) receive their gradient from the step's autograd node; checked against oracle autograd."""
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import get_loss
+    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
+    cfg = dict(cfg, head=0)
+    sd = {k: v for k, v in sd.items() if not k.startswith("binary_head")}
+    m = _build(cfg, sd)
+    m.enable_autograd(True)
+    scale = torch.nn.Parameter(torch.ones(512, device=DEV))
+    text0 = torch.from_numpy(batch["text"]).to(DEV)
+    video = torch.from_numpy(batch["video"]).to(DEV).requires_grad_(True)
+    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
+    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
+    text = text0 * scale
+    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    res = get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}, video, text,
+                   vpm.float(), tpm.float(), out, _args(), None)
+    res["loss"].backward()
+    torch.cuda.synchronize()
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"])
+    scale_r = torch.ones(512, requires_grad=True)
+    video_r = torch.from_numpy(batch["video"]).clone().requires_grad_(True)
+    ro = orc.forward(video_r, torch.from_numpy(batch["text"]) * scale_r, batch["video_padding_mask"],
+                     batch["text_padding_mask"])
+    O.get_loss_init(ro["logits_dual"], ro["logits_joint"], batch["start"], batch["end"],
+                    batch["text_padding_mask"])["loss"].backward()
+    for got, ref in ((scale.grad, scale_r.grad), (video.grad, video_r.grad)):
+        g, r = got.detach().float().cpu().double().reshape(-1), ref.double().reshape(-1)
+        cos = float((g @ r) / (g.norm() * r.norm()))
+        rel = float((g - r).norm() / r.norm())
+        assert cos > 0.999 and rel < 3e-2, (cos, rel)

@@ -166,3 +166,38 @@ def test_clip_gradients_matches_reference():
         assert (pa.grad is None) == (pb.grad is None)
         if pa.grad is not None:
             assert torch.equal(pa.grad, pb.grad)
+
+
+def test_gradients_reach_the_text_and_video_inputs(monkeypatch):
+    """The text backbone trains THROUGH `lang_embed` in the reference (train/main.py:58-60: fc1 / fc2 of the word2vec
+    module are ordinary parameters): inputs that require grad get their gradient from the step's autograd node."""
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import get_loss
+    cpu_ops.install(monkeypatch)
+    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
+    sd = {k: v for k, v in sd.items() if not k.startswith("binary_head")}
+    m = _model(cfg, sd, random_pos_start=0)
+    # upstream of the path: a toy "text backbone" whose parameter must receive a gradient through lang_embed
+    scale = torch.nn.Parameter(torch.ones(512))
+    text0 = torch.from_numpy(batch["text"])
+    video = torch.from_numpy(batch["video"]).clone().requires_grad_(True)
+    vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+    text = text0 * scale
+    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
+    res = get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}, video, text,
+                   vpm.float(), tpm.float(), out, _args(), None, shard_batch=False)
+    res["loss"].backward()
+    assert scale.grad is not None and video.grad is not None
+    # oracle
+    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"])
+    scale_r = torch.ones(512, requires_grad=True)
+    video_r = torch.from_numpy(batch["video"]).clone().requires_grad_(True)
+    ro = orc.forward(video_r, text0 * scale_r, batch["video_padding_mask"], batch["text_padding_mask"])
+    O.get_loss_init(ro["logits_dual"], ro["logits_joint"], batch["start"], batch["end"],
+                    batch["text_padding_mask"])["loss"].backward()
+    for got, ref in ((scale.grad, scale_r.grad), (video.grad, video_r.grad)):
+        g, r = got.double().reshape(-1), ref.double().reshape(-1)
+        cos = float((g @ r) / (g.norm() * r.norm()))
+        rel = float((g - r).norm() / r.norm())
+        assert cos > 0.999 and rel < 3e-2, (cos, rel)
