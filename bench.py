@@ -320,6 +320,9 @@ def run_gpu_arm(args):
     if world == 1 and not args.skip_train:
         extra["train_step"] = train_step_leg(runner, min(steps, 5), flush, fl, tf_peak)
 
+    if rank == 0 and world == 1 and args.eager_gpu:
+        extra["eager_gpu_baseline"] = eager_gpu_baseline()
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         r = cpu_reference_clips_per_sec(3, 1)
@@ -375,6 +378,44 @@ def train_step_leg(runner, steps, flush, fl, tf_peak):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def eager_gpu_baseline(clips=32, steps=5):
+    """OPTIONAL leg (--eager-gpu): the torch port of the reference's path (oracle/tan_oracle.py: torch matmul /
+    softmax / layer_norm / logsumexp, i.e. cuBLAS + torch eager kernels) on the SAME B200, fp32 and under bf16
+    autocast, on a `clips`-clip sample of the workload (its logits are materialised, so the full batch does not
+    fit): SURVEY.md 8(d)'s "existing GPU kernel" bar.  A baseline measurement like cpu_baseline, never the product."""
+    import torch
+
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import synth
+    sd = {k: torch.from_numpy(v).cuda() for k, v in synth.make_state_dict(E_LAYERS, D_LAYERS, perturb=False).items()}
+    batch = synth.make_batch(clips, T_FRAMES, N_TEXT)
+    orc = O.TanOracle(sd, E_LAYERS, D_LAYERS)
+    orc.sd = sd
+    video, text = torch.from_numpy(batch["video"]).cuda(), torch.from_numpy(batch["text"]).cuda()
+    vpm = torch.from_numpy(batch["video_padding_mask"]).cuda()
+    tpm = torch.from_numpy(batch["text_padding_mask"]).cuda()
+    out = {}
+    for name, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+        try:
+            def step():
+                with torch.no_grad(), ctx:
+                    o = orc.forward(video, text, vpm, tpm)
+                    return O.get_loss_init(o["logits_dual"].float().cpu(), o["logits_joint"].float().cpu(), batch["start"],
+                                           batch["end"], batch["text_padding_mask"])["loss"]
+            step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            torch.cuda.synchronize()
+            out[name] = round(clips * steps / (time.perf_counter() - t0), 1)
+        except Exception as e:
+            out[name] = f"{type(e).__name__}: {e}"[:200]
+    out["unit"] = "clips/s"
+    out["sample"] = f"{clips} clips; encoders on the GPU (torch eager), the loss of the port on the host (its mask logic is CPU code)"
+    return out
+
+
 def hbm_nce_roofline(runner, peaks, flush):
     """tan_nce_from_logits on the materialised bf16 logits of this workload: algorithmic bytes =
     the logits read once; measured with CUDA events, L2 flushed."""
@@ -428,6 +469,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-hbm", action="store_true", help="skip the materialised-logits HBM roofline leg")
     ap.add_argument("--skip-train", action="store_true", help="skip the training-step (fwd+loss+bwd) leg")
+    ap.add_argument("--eager-gpu", action="store_true", help="also time the torch-eager port of the reference on the GPU (sample)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
