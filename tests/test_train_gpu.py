@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import CASES, case_inputs, compare_param_grads, oracle_param_grads
+from tests.helpers import case_inputs, compare_param_grads, oracle_param_grads
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
