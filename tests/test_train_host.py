@@ -201,3 +201,24 @@ def test_gradients_reach_the_text_and_video_inputs(monkeypatch):
         cos = float((g @ r) / (g.norm() * r.norm()))
         rel = float((g - r).norm() / r.norm())
         assert cos > 0.999 and rel < 3e-2, (cos, rel)
+
+
+def test_more_than_64_sentences_takes_the_unfused_similarity_gradient(monkeypatch):
+    """N > 64 (BASELINE config 4 has N = 128): tan_sim_grad_gemm keeps two target words per row, so train.py falls
+    back to tan_linear_bf16 + tan_sim_grad_tiles; same gradients."""
+    from temporalalignnet_b200 import synth
+    cpu_ops.install(monkeypatch)
+    calls = {"gemm": 0, "tiles": 0}
+    from temporalalignnet_b200 import ops
+    g0, t0 = ops.sim_grad_gemm, ops.sim_grad_tiles
+    monkeypatch.setattr(ops, "sim_grad_gemm", lambda *a, **k: (calls.__setitem__("gemm", calls["gemm"] + 1), g0(*a, **k))[1])
+    monkeypatch.setattr(ops, "sim_grad_tiles", lambda *a, **k: (calls.__setitem__("tiles", calls["tiles"] + 1), t0(*a, **k))[1])
+    cfg = dict(E=1, D=1, use_text_pos_enc=0)
+    sd = synth.make_state_dict(1, 1)
+    batch = synth.make_batch(2, 16, 70, seed=11)
+    ref_loss, ref_grads = oracle_param_grads(dict(cfg, head=0), sd, batch, _args())
+    m = _model(cfg, sd, random_pos_start=0)
+    _, res = _step(m, batch, _args())
+    assert calls["tiles"] > 0 and calls["gemm"] == 0
+    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss)
+    compare_param_grads(m, ref_grads)
