@@ -222,3 +222,36 @@ def test_more_than_64_sentences_takes_the_unfused_similarity_gradient(monkeypatc
     assert calls["tiles"] > 0 and calls["gemm"] == 0
     assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss)
     compare_param_grads(m, ref_grads)
+
+
+def test_compat_shim_classes_train_out_of_the_box(monkeypatch):
+    """`from tan_model import TemporalAligner` through temporalalignnet_b200/compat (what train/main.py:20-21 does):
+    the exported classes have the training step on, same names / state-dict keys as the base classes."""
+    import importlib
+    import os
+    import sys
+
+    import temporalalignnet_b200
+    from temporalalignnet_b200 import get_loss
+    cpu_ops.install(monkeypatch)
+    compat = os.path.join(os.path.dirname(temporalalignnet_b200.__file__), "compat")
+    monkeypatch.syspath_prepend(compat)
+    sys.modules.pop("tan_model", None)
+    tan_model = importlib.import_module("tan_model")
+    try:
+        assert tan_model.TemporalAligner.__name__ == "TemporalAligner"
+        cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
+        m = tan_model.TemporalAligner(num_encoder_layers=1, num_decoder_layers=1, random_pos_start=0)
+        assert set(m.state_dict()) == set(sd)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+        vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+        out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm, text_timestamp=None, abs_text_pos=None)
+        loss = get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}, video, text,
+                        vpm.float(), tpm.float(), out, _args(), None, shard_batch=False)["loss"]
+        assert loss.requires_grad                               # train/main.py:112 can call .backward()
+        tw = tan_model.TwinTemporalAligner(m=0.99, num_encoder_layers=1, num_decoder_layers=1)
+        assert tw.online._autograd_on and not tw.target._autograd_on
+        assert all(k.startswith(("online.", "target.")) for k in tw.state_dict())
+    finally:
+        sys.modules.pop("tan_model", None)
