@@ -255,3 +255,92 @@ def test_compat_shim_classes_train_out_of_the_box(monkeypatch):
         assert all(k.startswith(("online.", "target.")) for k in tw.state_dict())
     finally:
         sys.modules.pop("tan_model", None)
+
+
+def test_reference_training_loop_body_runs_against_the_drop_in_api(monkeypatch):
+    """train/main.py:46-127 restated line by line on synthetic data (ragged token lists -> lang_model -> padded text
+    embeddings -> forward -> get_loss with the reference's KEYWORD arguments -> backward -> clip -> AdamW step),
+    with the compat classes and a toy text backbone: the loop trains, and the text backbone learns through
+    `lang_embed` as in the reference."""
+    import importlib
+    import os
+    import sys
+    import types
+
+    from torch.nn.utils.rnn import pad_sequence
+
+    import temporalalignnet_b200
+    from temporalalignnet_b200 import synth
+    from temporalalignnet_b200.loss import get_loss, get_mask_from_time
+    from temporalalignnet_b200.train import clip_gradients
+    cpu_ops.install(monkeypatch)
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(temporalalignnet_b200.__file__), "compat"))
+    sys.modules.pop("tan_model", None)
+    tan_model = importlib.import_module("tan_model")
+
+    class ToyLang(torch.nn.Module):                       # stands in for Word2VecModel (model/word2vec_model.py:76-102)
+        def __init__(self):
+            super().__init__()
+            self.word_embd = torch.nn.Embedding(50, 64)
+            self.fc2 = torch.nn.Linear(64, 512)
+
+        def forward(self, input_ids, attention_mask=None):
+            x = self.word_embd(input_ids) * attention_mask[..., None].float()
+            return {"pooler_output": self.fc2(x.sum(1) / attention_mask.sum(1, keepdim=True).clamp(min=1).float())}
+
+    def pad_sequence_by_last(sequences):                  # data/loader_htm.py:13-23
+        out = sequences[0].new_zeros((len(sequences), max(s.size(0) for s in sequences)) + sequences[0].shape[1:])
+        for i, t in enumerate(sequences):
+            out[i, :t.size(0)] = t
+            out[i, t.size(0):] = t[-1]
+        return out
+
+    try:
+        torch.manual_seed(0)
+        device = "cpu"
+        args = types.SimpleNamespace(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep",
+                                     loss_threshold=0.0, use_alignability_head=0, optim_policy="default", clip_grad=3.0)
+        model = tan_model.TemporalAligner(num_encoder_layers=1, num_decoder_layers=1, sim="cos", language_model="word2vec",
+                                          pos_enc="learned", use_text_pos_enc=0, use_alignability_head=0,
+                                          random_pos_start=0, lang_module=ToyLang())
+        model.train()
+        optimizer = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3)
+        b = synth.make_batch(4, 32, 4, seed=3)
+        g = torch.Generator().manual_seed(1)
+        input_data = {"video": torch.from_numpy(b["video"]), "padding_mask": torch.from_numpy(b["video_padding_mask"]).float(),
+                      "start": b["start"], "end": b["end"], "text": b["text_str"],
+                      "token": [torch.randint(1, 50, (len(s), 6), generator=g) for s in b["start"]]}
+        losses = []
+        for idx in range(4):
+            video_seq = input_data["video"].to(device)
+            video_padding_mask = input_data["padding_mask"].to(device)
+            num_sentence_per_sample = [i.shape[0] for i in input_data["token"]]                      # :52-55
+            flatten_sentence_token = torch.concat([i.to(device) for i in input_data["token"]], 0).long()
+            text_embed = model.lang_model(input_ids=flatten_sentence_token,
+                                          attention_mask=flatten_sentence_token != 0)["pooler_output"]  # :58-60
+            text_embed = pad_sequence_by_last(torch.split(text_embed, num_sentence_per_sample, dim=0))
+            text_padding_mask = pad_sequence(torch.split(torch.zeros(flatten_sentence_token.shape[0], device=device),
+                                                         num_sentence_per_sample, dim=0), batch_first=True, padding_value=1)
+            B, T, _ = video_seq.shape
+            N = text_embed.shape[1]
+            binary_sentence_timestamp, _, _ = get_mask_from_time(input_data["start"], input_data["end"],
+                                                                 num_timestamp=T, num_text=N, device=device)
+            logits = model(video_seq, text_embed, video_padding_mask=video_padding_mask.bool(),
+                           lang_padding_mask=text_padding_mask.bool(), text_timestamp=binary_sentence_timestamp,
+                           abs_text_pos=None)                                                        # :81-87
+            loss_dict = get_loss(input_data=input_data, video_seq=video_seq, text_embed=text_embed,
+                                 video_padding_mask=video_padding_mask, text_padding_mask=text_padding_mask,
+                                 logits=logits, args=args, abs_text_pos=None)                        # :98-105
+            loss = loss_dict["loss"]
+            assert not torch.isinf(loss) and not torch.isnan(loss)
+            loss.backward()                                                                          # :112 (scale 1)
+            _ = clip_gradients(model, clip_grad=args.clip_grad)                                      # :115-116
+            if idx == 0:
+                assert model.bert.fc2.weight.grad is not None and float(model.bert.fc2.weight.grad.abs().sum()) > 0
+                assert model.bert.word_embd.weight.grad is not None
+            optimizer.step()
+            optimizer.zero_grad()
+            losses.append({k: v.item() for k, v in loss_dict.items()}["loss"])                        # :127
+        assert losses[-1] < losses[0], losses
+    finally:
+        sys.modules.pop("tan_model", None)
