@@ -22,5 +22,8 @@ struct AttnBwdArgs {
 
 // attention_bwd.cu
 int attention_bwd_mma(const AttnBwdArgs& a, cudaStream_t stream);
+// attention_bwd_pipe.cu (experimental cp.async-pipelined variant, TAN_ATTN_BWD=pipe)
+bool attention_bwd_pipe_supported(const AttnBwdArgs& a);
+int attention_bwd_mma_pipe(const AttnBwdArgs& a, cudaStream_t stream);
 
 }  // namespace tanb

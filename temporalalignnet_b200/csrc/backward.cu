@@ -885,6 +885,8 @@ extern "C" int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k,
   a.lse = lse; a.delta = delta;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
   static const bool use_wmma = [] { const char* e = getenv("TAN_ATTN_BWD"); return e != nullptr && e[0] == 'w'; }();
+  static const bool use_pipe = [] { const char* e = getenv("TAN_ATTN_BWD"); return e != nullptr && e[0] == 'p'; }();
+  if (use_pipe && attention_bwd_pipe_supported(a)) return attention_bwd_mma_pipe(a, static_cast<cudaStream_t>(stream));
   if (!use_wmma) return attention_bwd_mma(a, static_cast<cudaStream_t>(stream));
   const int smem = static_cast<int>(sizeof(AttnBwdSmem)) + 128;
   TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

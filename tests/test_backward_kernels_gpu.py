@@ -291,3 +291,19 @@ def test_sim_grad_tiles_and_gemms(with_kill):
     for got, ref in ((dA, af.grad), (dB, tf.grad)):
         err = ((got - ref).norm() / ref.norm()).item()
         assert err < 1e-2, err                                  # G is bf16 (2^-9 per element, averaged)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TAN_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental cp.async-pipelined attention backward (TAN_ATTN_BWD=pipe): not the default; "
+                           "run with TAN_TEST_EXPERIMENTAL=1 to validate it")
+def test_attention_bwd_pipelined_variant():
+    """Re-runs test_attention_bwd in a child process with TAN_ATTN_BWD=pipe (the selection is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, TAN_ATTN_BWD="pipe")
+    env.pop("TAN_TEST_EXPERIMENTAL", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-k", "test_attention_bwd",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
