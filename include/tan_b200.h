@@ -338,6 +338,15 @@ TAN_API int tan_sim_grad_gemm(const void* vfeat, int64_t ldv, const void* tfeat,
                               const uint8_t* row_kill, const float* ra, const float* rap, const float* cb,
                               const float* cbp, void* G, int64_t ldg, void* stream);
 
+/* EXPERIMENTAL (round 1: compiled, not yet run on a GPU; train.py uses it only with TAN_SIM_GRAD_GT=1):
+ * tan_sim_grad_gemm that also writes GT [C_pad, ldgt] = G^T from the epilogue (rows Rc .. Rc_pad zero), which makes
+ * the tan_transpose_bf16 pass over G unnecessary. */
+TAN_API int tan_sim_grad_gemm_gt(const void* vfeat, int64_t ldv, const void* tfeat, int64_t ldt, int Rc, int r0,
+                                 const tan_sim_geom* g, int C_pad, const uint32_t* posbits, const uint8_t* col_valid,
+                                 const uint8_t* row_kill, const float* ra, const float* rap, const float* cb,
+                                 const float* cbp, void* G, int64_t ldg, void* GT, int64_t ldgt, int Rc_pad,
+                                 void* stream);
+
 /* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
  * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
  * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from

@@ -430,12 +430,22 @@ def sim_grad_tiles(z: torch.Tensor, Rc: int, r0: int, g: SimGeom, posbits, col_v
 
 
 def sim_grad_gemm(a: torch.Tensor, t_pad: torch.Tensor, r0: int, g: SimGeom, posbits, col_valid, row_kill, ra, rap, cb,
-                  cbp, G: torch.Tensor) -> None:
-    """tan_sim_grad_gemm: a [Rc, d] bf16 video rows, t_pad [Cp, d] bf16 text rows (zero beyond C) -> G [Rc, Cp] bf16."""
+                  cbp, G: torch.Tensor, GT: Optional[torch.Tensor] = None) -> None:
+    """tan_sim_grad_gemm: a [Rc, d] bf16 video rows, t_pad [Cp, d] bf16 text rows (zero beyond C) -> G [Rc, Cp] bf16.
+    GT [Cp, pad64(Rc)] (experimental tan_sim_grad_gemm_gt): also the transposed copy, written by the epilogue."""
     global _launches
     Rc, d = a.shape
     Cp = t_pad.shape[0]
     if _skip("sim_bwd", 2.0 * Rc * Cp * d):
+        return
+    if GT is not None:
+        with _timed("sim_bwd", 2.0 * Rc * Cp * d):
+            check(lib().tan_sim_grad_gemm_gt(a.data_ptr(), a.stride(0), t_pad.data_ptr(), t_pad.stride(0), Rc, r0,
+                                             C.byref(g), Cp, posbits.data_ptr(), col_valid.data_ptr(), _ptr(row_kill),
+                                             ra.data_ptr(), rap.data_ptr(), cb.data_ptr(), cbp.data_ptr(), G.data_ptr(),
+                                             G.stride(0), GT.data_ptr(), GT.stride(0), pad64(Rc), _stream()),
+                  "tan_sim_grad_gemm_gt")
+        _launches += 1
         return
     with _timed("sim_bwd", 2.0 * Rc * Cp * d):
         check(lib().tan_sim_grad_gemm(a.data_ptr(), a.stride(0), t_pad.data_ptr(), t_pad.stride(0), Rc, r0, C.byref(g), Cp,

@@ -29,6 +29,7 @@ from .tfm_model import StageSink, _f32, _mask_u8
 AUTOGRAD_DEFAULT = os.environ.get("TAN_AUTOGRAD", "0") != "0"
 SIM_BWD_ROWS = 8192          # rows of one similarity-gradient chunk (z chunk = rows x C fp32)
 SIM_GRAD_FUSED = os.environ.get("TAN_SIM_GRAD_FUSED", "1") != "0"     # G in the epilogue of the recomputation GEMM
+SIM_GRAD_GT = os.environ.get("TAN_SIM_GRAD_GT", "0") == "1"           # experimental: G^T from the same epilogue
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -429,7 +430,10 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
         for r0 in range(0, R, Rc):
             rc = min(Rc, R - r0)
             a = vsm[s, r0:r0 + rc]
-            if fused:      # cosines recomputed and turned into G inside one GEMM; G^T by the transpose kernel
+            if fused and SIM_GRAD_GT:     # experimental: the epilogue writes G^T as well (no transpose pass)
+                ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
+                                  G[:rc], GT=GT[:, :ops.pad64(rc)])
+            elif fused:    # cosines recomputed and turned into G inside one GEMM; G^T by the transpose kernel
                 ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
                                   G[:rc])
                 ops.transpose_bf16(G[:rc], GT[:, :ops.pad64(rc)])

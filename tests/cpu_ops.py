@@ -198,11 +198,14 @@ def _grad_matrix(cos, Rc, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp)
     return e * (ra[rr][:, None] + cb[None, :g.C] - pos * (rap[rr][:, None] + cbp[None, :g.C])) / 0.07
 
 
-def sim_grad_gemm(a, t_pad, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G):
+def sim_grad_gemm(a, t_pad, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G, GT=None):
     Rc = a.shape[0]
     Gm = _grad_matrix(a.float() @ t_pad.float().t(), Rc, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp)
     G.zero_()
     G[:, :g.C] = Gm.to(BF)
+    if GT is not None:
+        GT.zero_()
+        GT[:g.C, :Rc] = Gm.to(BF).t()
 
 
 def sim_grad_tiles(z, Rc, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G, GT):

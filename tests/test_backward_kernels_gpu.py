@@ -281,6 +281,13 @@ def test_sim_grad_tiles_and_gemms(with_kill):
     assert (G2[:, C:] == 0).all()
     assert ((G2.float() - G.float()).norm() / G.float().norm()).item() < 1e-2
     assert (G2.float() - G.float()).abs().max().item() < 2e-2 * G.float().abs().max().item()
+    if __import__("os").environ.get("TAN_TEST_EXPERIMENTAL") == "1":     # experimental epilogue that also writes G^T
+        G3 = torch.full((R, Cp), 3.0, dtype=torch.bfloat16, device=DEV)
+        GT3 = torch.full((Cp, ops.pad64(R)), 3.0, dtype=torch.bfloat16, device=DEV)
+        ops.sim_grad_gemm(a, tpad, 0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp, G3, GT=GT3)
+        torch.cuda.synchronize()
+        assert torch.equal(G3, G2)
+        assert torch.equal(GT3[:, :R], G2.t()) and (GT3[:, R:] == 0).all()
     tT = ops.transpose_bf16(tpad)                               # [d, Cp]
     aT = ops.transpose_bf16(a)                                  # [d, pad64(R)]
     dA = torch.empty(R, d, dtype=torch.float32, device=DEV)
