@@ -347,6 +347,14 @@ TAN_API int tan_sim_grad_gemm_gt(const void* vfeat, int64_t ldv, const void* tfe
                                  const float* cbp, void* G, int64_t ldg, void* GT, int64_t ldgt, int Rc_pad,
                                  void* stream);
 
+/* EXPERIMENTAL (round 1: compiled, not yet run on a GPU; train.py uses it only with TAN_FUSE_BIAS_SUM=1):
+ * tan_transpose_bf16 that also produces colsum[c] (+)= sum_r in[r, c] -- the bias gradient of the dY whose transpose
+ * feeds the weight-gradient GEMM -- in the same pass (deterministic per-tile partials through `workspace`). */
+TAN_API size_t tan_transpose_colsum_workspace_bytes(int R, int C);
+TAN_API int tan_transpose_colsum_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int R_pad,
+                                      float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
  * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
  * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from

@@ -340,6 +340,24 @@ def transpose_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     return out
 
 
+def transpose_colsum_bf16(x: torch.Tensor, colsum_out: torch.Tensor, accumulate: bool = True) -> torch.Tensor:
+    """tan_transpose_colsum_bf16 (experimental): transpose_bf16(x) and colsum_out (+)= column sums of x in one pass."""
+    global _launches
+    R, Ccols = x.shape
+    Rp = pad64(R)
+    out = torch.empty(Ccols, Rp, dtype=torch.bfloat16, device=x.device)
+    if _skip("bwd_glue", 2.0 * R * Ccols):
+        return out
+    nbytes = int(lib().tan_transpose_colsum_workspace_bytes(R, Ccols))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    with _timed("transpose", 0.0):
+        check(lib().tan_transpose_colsum_bf16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), R, Ccols, Rp,
+                                              colsum_out.data_ptr(), int(bool(accumulate)), ws.data_ptr(), nbytes,
+                                              _stream()), "tan_transpose_colsum_bf16")
+    _launches += 2
+    return out
+
+
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = True) -> None:
     """tan_colsum: out [N] fp32 (+)= column sums of x [M, N] (bf16 or fp32)."""
     global _launches

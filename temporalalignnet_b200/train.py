@@ -261,13 +261,22 @@ def _streams(dev, n: int):
     return pool[:n]
 
 
-def _wgrad(dy_bf16: torch.Tensor, x_bf16: torch.Tensor, gw: torch.Tensor) -> None:
+FUSE_BIAS_SUM = os.environ.get("TAN_FUSE_BIAS_SUM", "0") == "1"     # experimental: bias sums inside the dY transpose
+
+
+def _wgrad(dy_bf16: torch.Tensor, x_bf16: torch.Tensor, gw: torch.Tensor, gb: Optional[torch.Tensor] = None) -> None:
     """gw [N, K] += dy^T @ x   (dy [M, N], x [M, K] bf16): the pair GEMM on the two transposes with fp32
     accumulation.  A weight gradient has few output tiles (4 .. 16 of 256 x 256) and a long contraction (all tokens),
     so one launch would occupy 4 .. 16 of the 74 CTA pairs: the contraction is split into chunks that run as
     concurrent launches on side streams (each launch only takes as many CTA pairs as it has tiles) into partial
-    buffers, summed in a fixed order by tan_colsum (deterministic)."""
-    dyT = ops.transpose_bf16(dy_bf16)          # [N, pad64(M)]
+    buffers, summed in a fixed order by tan_colsum (deterministic).  gb [N]: the bias gradient (column sums of dy),
+    accumulated by tan_colsum or, experimentally, by the transpose of dy itself."""
+    if gb is not None and FUSE_BIAS_SUM:
+        dyT = ops.transpose_colsum_bf16(dy_bf16, gb)
+    else:
+        if gb is not None:
+            ops.colsum(dy_bf16, gb)
+        dyT = ops.transpose_bf16(dy_bf16)      # [N, pad64(M)]
     xT = ops.transpose_bf16(x_bf16)            # [K, pad64(M)]
     N, Mp = dyT.shape
     K = xT.shape[0]
@@ -326,27 +335,23 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
         H = blk.n_head
         # ---- MLP: x_out = x1 + c_proj(gelu(c_fc(ln_2(x1)))) ------------------------------------------
         ops.cast_bf16(dx, dxb)
-        ops.colsum(dxb, grads.of(blk.mlp.c_proj.bias))
         _dgrad(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), out_bf16=dh)
-        _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight))
+        _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
         ops.quickgelu_bwd(dh, lt.u, dh)                                        # du, in place
-        ops.colsum(dh, grads.of(blk.mlp.c_fc.bias))
         _dgrad(dh, ops.transpose_bf16(cache.get(blk.mlp.c_fc.weight)), out_f32=dy32)
-        _wgrad(dh, lt.xn2, grads.of(blk.mlp.c_fc.weight))
+        _wgrad(dh, lt.xn2, grads.of(blk.mlp.c_fc.weight), grads.of(blk.mlp.c_fc.bias))
         ops.layernorm_bwd(dy32, lt.x1, _f32(blk.ln_2.weight), dx, True, M, d, grads.of(blk.ln_2.weight),
                           grads.of(blk.ln_2.bias))
         # ---- attention: x1 = x + out_proj(attn(in_proj(ln_1(x)))) --------------------------------------
         ops.cast_bf16(dx, dxb)
-        ops.colsum(dxb, grads.of(blk.attn.out_proj.bias))
         _dgrad(dxb, ops.transpose_bf16(cache.get(blk.attn.out_proj.weight)), out_bf16=datt)
-        _wgrad(dxb, lt.att, grads.of(blk.attn.out_proj.weight))
+        _wgrad(dxb, lt.att, grads.of(blk.attn.out_proj.weight), grads.of(blk.attn.out_proj.bias))
         q, k, v = lt.qkv[:, 0:d], lt.qkv[:, d:2 * d], lt.qkv[:, 2 * d:3 * d]
         ops.attention_bwd(q, k, v, lt.att, datt, tape.kpm, dqkv[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:3 * d], lse,
                           delta, B, H, L, L)
-        ops.colsum(dqkv, grads.of(blk.attn.in_proj_bias))
         sg = stage_grads[i - 1] if i >= 1 else None      # ln_1 of block i IS stage i-1 (model/tfm_model.py:50-53)
         _dgrad(dqkv, ops.transpose_bf16(cache.get(blk.attn.in_proj_weight)), out_f32=dy32, residual=sg)
-        _wgrad(dqkv, lt.xn, grads.of(blk.attn.in_proj_weight))
+        _wgrad(dqkv, lt.xn, grads.of(blk.attn.in_proj_weight), grads.of(blk.attn.in_proj_bias))
         ops.layernorm_bwd(dy32, lt.x_in, _f32(blk.ln_1.weight), dx, True, M, d, grads.of(blk.ln_1.weight),
                           grads.of(blk.ln_1.bias))
     return dx

@@ -314,3 +314,17 @@ def test_attention_bwd_pipelined_variant():
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TAN_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental fused transpose + bias sums (TAN_FUSE_BIAS_SUM=1): not the default")
+@pytest.mark.parametrize("R,C", [(144, 512), (1000, 1536), (70000, 2048), (64, 2)])
+def test_transpose_colsum_experimental(R, C):
+    ops = _ops()
+    x = _rand(R, C, seed=41).to(torch.bfloat16)
+    bias = torch.ones(C, dtype=torch.float32, device=DEV)
+    out = ops.transpose_colsum_bf16(x, bias, accumulate=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :R], x.t()) and (out[:, R:] == 0).all()
+    ref = 1.0 + x.double().sum(0)
+    assert (bias.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
