@@ -355,6 +355,17 @@ TAN_API int tan_transpose_colsum_bf16(const void* in, int64_t ldi, void* out, in
                                       float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
                                       void* stream);
 
+/* out[P, Q] (+)= A[R, P]^T @ B[R, Q]: bf16 row-major operands consumed as they lie in HBM (MN-major UMMA operands,
+ * no transposes), the contraction running over their R rows; fp32 accumulation and output (row pitch ldo; added to
+ * the existing contents when accumulate != 0).  Weight gradients dW = dY^T X (autograd of F.linear,
+ * model/tfm_model.py:21,35-37, model/tan_model.py:155,:232) and the text-side similarity gradient dB = G^T V
+ * (autograd of the einsum at model/tan_model.py:119,:139).  The contraction is split over the CTA pairs inside the
+ * launch; partial tiles go through `workspace` (tan_gemm_tn_workspace_bytes; may be 0) and are summed in a fixed
+ * order (deterministic).  P % 8 == 0, Q % 32 == 0, lda / ldb multiples of 8, ldo of 4. */
+TAN_API size_t tan_gemm_tn_workspace_bytes(int R, int P, int Q);
+TAN_API int tan_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int R, int P, int Q, float* out,
+                             int64_t ldo, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
  * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
  * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from

@@ -18,7 +18,7 @@ TAN_OK = 0
 ERR_NAMES = {-1: "TAN_ERR_SHAPE", -2: "TAN_ERR_ARCH", -3: "TAN_ERR_WORKSPACE", -4: "TAN_ERR_CUDA",
              -5: "TAN_ERR_ARG"}
 ACT_NONE, ACT_QUICKGELU = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class TanError(RuntimeError):
@@ -111,6 +111,9 @@ SIGNATURES = {
     "tan_transpose_colsum_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "tan_transpose_colsum_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tan_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "tan_gemm_tn_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "tan_attention_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -359,11 +359,7 @@ extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int
   TAN_CHECK(make_tmap_2d(&tmQ, q, 2, static_cast<uint64_t>(B) * Lq, static_cast<uint64_t>(H) * 64, ldq, kAttBQ));
   TAN_CHECK(make_tmap_2d(&tmK, k, 2, static_cast<uint64_t>(B) * Lk, static_cast<uint64_t>(H) * 64, ldk, kAttBK));
   TAN_CHECK(make_tmap_2d(&tmV, v, 2, static_cast<uint64_t>(B) * Lk, static_cast<uint64_t>(H) * 64, ldv, kAttBK));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAN_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-    attr_set = true;
-  }
+  TAN_CHECK(set_max_dyn_smem(reinterpret_cast<const void*>(attention_kernel), kAttSmem));
   // one CTA per (clip, head) when that fills the GPU (2 CTAs per SM); otherwise split the query tiles over
   // blockIdx.z so that short batches of long sequences still occupy every SM
   const int nq_total = (Lq + kAttBQ - 1) / kAttBQ;

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -53,6 +54,24 @@ static DevInfo* dev_info() {
 int num_sms() {
   DevInfo* d = dev_info();
   return (d && d->sms > 0) ? d->sms : 148;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember (device, kernel)
+// pairs, so that one process driving several GPUs sets it on each of them (a per-process flag would leave the
+// second device at the 48 KB default and its first launch would fail).
+int set_max_dyn_smem(const void* kernel, int bytes) {
+  struct Entry { int dev; const void* kernel; };
+  static Entry done[512];
+  static int n_done = 0;
+  static std::mutex mu;
+  int dev = 0;
+  TAN_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i].dev == dev && done[i].kernel == kernel) return TAN_OK;
+  TAN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (n_done < 512) done[n_done++] = Entry{dev, kernel};
+  return TAN_OK;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -146,7 +165,7 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint4* __res
 
 using namespace tanb;
 
-extern "C" int tan_abi_version(void) { return 3; }
+extern "C" int tan_abi_version(void) { return 4; }
 
 extern "C" const char* tan_last_error_string(void) { return g_err; }
 

@@ -20,6 +20,8 @@ typedef __nv_bfloat16 bf16;
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+// per-device cudaFuncAttributeMaxDynamicSharedMemorySize (capi.cu)
+int set_max_dyn_smem(const void* kernel, int bytes);
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency).
 // 2-D row-major bf16 tensor [rows, cols] (cols contiguous, row pitch `ld` elements), box
 // [box_rows, box_cols], 128-byte swizzle (box_cols * 2 must be 128).

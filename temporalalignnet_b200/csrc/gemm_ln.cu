@@ -411,11 +411,7 @@ static int launch_res_ln(const void* A, int64_t lda, const void* W, int64_t ldw,
       TAN_CHECK(make_tmap_2d(&tmNB, nrmB, 2, (clips - 1) * strideB + (p.L - p.l_split), N, N, 32));
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    TAN_CUDA(cudaFuncSetAttribute(gemm_res_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnSmem));
-    attr_set = true;
-  }
+  TAN_CHECK(set_max_dyn_smem(reinterpret_cast<const void*>(gemm_res_ln_kernel), kLnSmem));
   const int max_pairs = num_sms() / 2;
   const int pairs = p.n_tiles < max_pairs ? p.n_tiles : max_pairs;
   return launch_pdl(gemm_res_ln_kernel, dim3(2 * pairs), dim3(kLnThreads), kLnSmem, static_cast<cudaStream_t>(stream), 2,

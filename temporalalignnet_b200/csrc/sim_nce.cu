@@ -992,11 +992,7 @@ extern "C" int tan_sim_nce_fwd(const void* vfeat, const void* tfeat, int64_t tfe
     f.num_kb = g->d / kG2BK;
     f.row_part = row_part;
     f.col_part = col_part;
-    static bool attr_set = false;
-    if (!attr_set) {
-      TAN_CUDA(cudaFuncSetAttribute(sim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmem));
-      attr_set = true;
-    }
+    TAN_CHECK(set_max_dyn_smem(reinterpret_cast<const void*>(sim_fused_kernel), kSfSmem));
     const int64_t tasks = static_cast<int64_t>(pair_m_tiles) * f.col_chunks;
     const int pairs = static_cast<int>(tasks < max_pairs ? tasks : max_pairs);
     TAN_CHECK(launch_pdl(sim_fused_kernel, dim3(2 * pairs), dim3(kSfThreads), kSfSmem, st, 2, tmA, tmB, f));

@@ -232,11 +232,7 @@ int launch_umma_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   auto kern = umma_gemm2_kernel<Epi>;
   constexpr int smem = gemm2_smem_bytes<Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    TAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  TAN_CHECK(set_max_dyn_smem(reinterpret_cast<const void*>(kern), smem));
   const int max_pairs = num_sms() / 2;
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
   return launch_pdl(kern, dim3(2 * pairs, 1, 1), dim3(kG2Threads, 1, 1), smem, stream, 2, tmA, tmB, tmOut, tmAux,

@@ -358,6 +358,31 @@ def transpose_colsum_bf16(x: torch.Tensor, colsum_out: torch.Tensor, accumulate:
     return out
 
 
+_tn_ws = {}
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, accumulate: bool = True, tag: str = "wgrad") -> None:
+    """tan_gemm_tn_bf16: out [P, Q] fp32 (+)= a[R, P]^T @ b[R, Q] (a, b bf16 row-major, row pitch may exceed the
+    width): weight gradients and the text-side similarity gradient without transposes."""
+    global _launches
+    R, P = a.shape
+    Q = b.shape[1]
+    if _skip(tag, 2.0 * R * P * Q):
+        return
+    nbytes = int(lib().tan_gemm_tn_workspace_bytes(R, P, Q))
+    ws = None
+    if nbytes:
+        key = (str(a.device), torch.cuda.current_stream().cuda_stream)
+        ws = _tn_ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = _tn_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+    with _timed(tag, 2.0 * R * P * Q):
+        check(lib().tan_gemm_tn_bf16(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), R, P, Q, out.data_ptr(),
+                                     out.stride(0), int(bool(accumulate)), _ptr(ws), nbytes, _stream()),
+              "tan_gemm_tn_bf16")
+    _launches += 2 if nbytes else 1
+
+
 def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = True) -> None:
     """tan_colsum: out [N] fp32 (+)= column sums of x [M, N] (bf16 or fp32)."""
     global _launches

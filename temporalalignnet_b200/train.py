@@ -30,6 +30,8 @@ AUTOGRAD_DEFAULT = os.environ.get("TAN_AUTOGRAD", "0") != "0"
 SIM_BWD_ROWS = 8192          # rows of one similarity-gradient chunk (z chunk = rows x C fp32)
 SIM_GRAD_FUSED = os.environ.get("TAN_SIM_GRAD_FUSED", "1") != "0"     # G in the epilogue of the recomputation GEMM
 SIM_GRAD_GT = os.environ.get("TAN_SIM_GRAD_GT", "0") == "1"           # experimental: G^T from the same epilogue
+# weight gradients / the text-side similarity gradient on MN-major operands (tan_gemm_tn_bf16): no transposes
+TN_GEMM = os.environ.get("TAN_TN_GEMM", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -271,6 +273,11 @@ def _wgrad(dy_bf16: torch.Tensor, x_bf16: torch.Tensor, gw: torch.Tensor, gb: Op
     concurrent launches on side streams (each launch only takes as many CTA pairs as it has tiles) into partial
     buffers, summed in a fixed order by tan_colsum (deterministic).  gb [N]: the bias gradient (column sums of dy),
     accumulated by tan_colsum or, experimentally, by the transpose of dy itself."""
+    if TN_GEMM and dy_bf16.shape[1] % 8 == 0 and x_bf16.shape[1] % 32 == 0:
+        if gb is not None:
+            ops.colsum(dy_bf16, gb)
+        ops.gemm_tn(dy_bf16, x_bf16, gw, accumulate=True)
+        return
     if gb is not None and FUSE_BIAS_SUM:
         dyT = ops.transpose_colsum_bf16(dy_bf16, gb)
     else:
@@ -438,6 +445,14 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
             if fused and SIM_GRAD_GT:     # experimental: the epilogue writes G^T as well (no transpose pass)
                 ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
                                   G[:rc], GT=GT[:, :ops.pad64(rc)])
+            elif fused and TN_GEMM and d % 32 == 0:
+                # cosines recomputed and turned into G inside one GEMM; dB = G^T @ video straight from G and the
+                # video rows as they lie (MN-major operands): no transpose of either
+                ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
+                                  G[:rc])
+                ops.linear(G[:rc], tT, out_f32=d_v[s, r0:r0 + rc], tag="sim_bwd")                # dA = G @ text
+                ops.gemm_tn(G[:rc], a, d_t[si], accumulate=True, tag="sim_bwd")                  # dB += G^T @ video
+                continue
             elif fused:    # cosines recomputed and turned into G inside one GEMM; G^T by the transpose kernel
                 ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
                                   G[:rc])

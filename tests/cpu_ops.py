@@ -140,6 +140,11 @@ def transpose_colsum_bf16(x, colsum_out, accumulate=True):
     return transpose_bf16(x)
 
 
+def gemm_tn(a, b, out, accumulate=True, tag="wgrad"):
+    r = a.float().t() @ b.float()
+    out.copy_(out + r if accumulate else r)
+
+
 def colsum(x, out, accumulate=True):
     s = x.float().sum(0)
     out.copy_(out + s if accumulate else s)
@@ -286,7 +291,7 @@ def agree_scan(own, posbits, vpm_u8, tpm_u8, B, T, N, fill_max):
     return win, torch.zeros(B, N), z.max(dim=1).values
 
 
-NAMES = ["own_clip_sim", "agree_scan", "transpose_colsum_bf16", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
+NAMES = ["gemm_tn", "own_clip_sim", "agree_scan", "transpose_colsum_bf16", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
          "transpose_bf16", "colsum", "layernorm_bwd", "l2norm_bwd", "batch_sum", "sim_grad_gemm", "sim_grad_tiles",
          "pos_from_time", "sim_workspace_bytes", "sim_nce_fwd", "nce_reduce"]
 

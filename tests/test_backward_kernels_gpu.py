@@ -328,3 +328,33 @@ def test_transpose_colsum_experimental(R, C):
     assert torch.equal(out[:, :R], x.t()) and (out[:, R:] == 0).all()
     ref = 1.0 + x.double().sum(0)
     assert (bias.double() - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("R,P,Q,acc", [(64, 64, 64, False), (1000, 512, 512, True), (4096, 1536, 512, False),
+                                       (8200, 512, 2048, True), (300, 24, 128, True), (20000, 512, 1024, False),
+                                       (8192, 1024, 512, True)])
+def test_gemm_tn(R, P, Q, acc):
+    """out (+)= a^T @ b on MN-major operands (no transposes) vs torch fp32 matmul of the same bf16 inputs."""
+    ops = _ops()
+    a = _rand(R, P, seed=31).to(torch.bfloat16)
+    b = _rand(R, Q, seed=32).to(torch.bfloat16)
+    out0 = _rand(P, Q, seed=33)
+    out = out0.clone()
+    ops.gemm_tn(a, b, out, accumulate=acc)
+    ref = a.float().t() @ b.float() + (out0 if acc else 0)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+    # deterministic: same bits on a second run
+    out2 = out0.clone()
+    ops.gemm_tn(a, b, out2, accumulate=acc)
+    assert torch.equal(out, out2)
+
+
+def test_gemm_tn_pitched_operands():
+    ops = _ops()
+    big = _rand(3000, 1536, seed=34).to(torch.bfloat16)
+    a, b = big[:, 512:1024], big[:, 1024:1536]
+    out = torch.zeros(512, 512, dtype=torch.float32, device=DEV)
+    ops.gemm_tn(a, b, out, accumulate=False)
+    ref = a.float().t() @ b.float()
+    assert (out - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
