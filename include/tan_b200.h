@@ -162,10 +162,13 @@ TAN_API int tan_layernorm(const tan_ln_args* args, void* stream);
  * torch.softmax over all -inf does in the reference.
  * Replaces F.scaled_dot_product_attention + the [L,B,C]<->[B*H,L,hd] transposes reached from
  * nn.MultiheadAttention at model/tfm_model.py:32 (self-attention, Lq == Lk) and :80
- * (cross-attention of the unused decoder, Lq != Lk). */
+ * (cross-attention of the unused decoder, Lq != Lk).
+ * lse (optional, may be NULL): [B, H, pad64(Lq)] fp32, receives the log2-domain log-sum-exp of every query row's
+ * scaled scores, log2(sum_j exp(q_i . k_j / 8)) (+inf in the padding rows Lq .. pad64(Lq)): what
+ * tan_attention_bwd_bf16 needs from the forward pass (pad64(n) = n rounded up to a multiple of 64). */
 TAN_API int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                       const uint8_t* key_padding_mask, void* out, int64_t ldo, int B, int H, int Lq,
-                       int Lk, void* stream);
+                               const uint8_t* key_padding_mask, void* out, int64_t ldo, int B, int H, int Lq, int Lk,
+                               float* lse, void* stream);
 
 /* ---- cosine-similarity matrix + MIL-NCE statistics ----------------------------------------------- */
 
@@ -366,15 +369,51 @@ TAN_API size_t tan_gemm_tn_workspace_bytes(int R, int P, int Q);
 TAN_API int tan_gemm_tn_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int R, int P, int Q, float* out,
                              int64_t ldo, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient):
- * writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16) and the per-row statistics lse / delta [B, H, Lq] fp32 it
- * recomputes.  Deterministic (no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from
+/* Backward of tan_attention_bf16 (same operand conventions; o = the forward output, d_out its gradient) on tcgen05
+ * tensor cores: writes dq [B*Lq, *], dk / dv [B*Lk, *] (bf16).  lse [B, H, pad64(Lq)] fp32 is the row statistic the
+ * FORWARD call stored (16-byte aligned); delta [B, H, pad64(Lq)] fp32 is workspace (receives <d_out_i, o_i>).
+ * Deterministic (two kernels, no atomics).  Replaces autograd of F.scaled_dot_product_attention reached from
  * model/tfm_model.py:32. */
 TAN_API int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                    const void* o, int64_t ldo, const void* d_out, int64_t lddo,
                                    const uint8_t* key_padding_mask, void* dq, int64_t lddq, void* dk, int64_t lddk,
                                    void* dv, int64_t lddv, float* lse, float* delta, int B, int H, int Lq, int Lk,
                                    void* stream);
+
+/* ---- optimizer step (co-training step) ------------------------------------------ */
+
+/* One parameter tensor of the multi-tensor optimizer step (all pointers device, fp32, numel elements). */
+typedef struct {
+  float* param;
+  const float* grad;       /* NULL: no gradient this step, the tensor is skipped (as torch does) */
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* ema;              /* NULL or the EMA target copy: ema = m * ema + (1 - m) * param_new */
+  int64_t numel;
+  float decay;             /* 1 - lr * weight_decay of the tensor's parameter group */
+  float neg_step_size;     /* -lr / (1 - beta1^step) */
+} tan_optim_tensor;
+
+/* Per-parameter gradient clipping (utils/train_utils.py:3-13: g *= min(1, clip / (||g|| + 1e-6)); clip_grad <= 0
+ * disables), AdamW (torch.optim.AdamW as constructed at train/main.py:397, decoupled weight decay) and the EMA
+ * update of the target network (model/tan_model.py:340-344) over ALL tensors of `table` [n_tensors] in two launches,
+ * no host synchronisation.  Chunking (built by the caller): chunk j covers elements [chunk_start[j],
+ * chunk_start[j] + chunk_elems) of tensor chunk_tensor[j]; the chunks of tensor t are tensor_first_chunk[t] ..
+ * tensor_first_chunk[t + 1].  partial [n_chunks] fp32 workspace; norms_out [n_tensors] (optional) receives the
+ * gradient norms (what clip_gradients returns); inv_scale (optional device scalar) multiplies the gradients first
+ * (GradScaler.unscale_, train/main.py:114).  An unclipped, unscaled step is bit-identical to
+ * torch.optim.AdamW(foreach=True) in fp32 (same operations, one rounding each; the hyper-parameters are doubles, as
+ * Python hands them to torch, and are rounded to fp32 where the tensor operation consumes them). */
+TAN_API int tan_optim_adamw_step(const tan_optim_tensor* table, int n_tensors, const int* chunk_tensor,
+                                 const int64_t* chunk_start, const int* tensor_first_chunk, int n_chunks,
+                                 int chunk_elems, double clip_grad, double beta1, double beta2, double eps, int step,
+                                 double ema_m, const float* inv_scale, float* partial, float* norms_out,
+                                 void* stream);
+
+/* ema = m * ema + (1 - m) * param for every tensor of `table` with a non-NULL ema (model/tan_model.py:340-344,
+ * TwinTemporalAligner._momentum_update), one launch. */
+TAN_API int tan_ema_update(const tan_optim_tensor* table, const int* chunk_tensor, const int64_t* chunk_start,
+                           int n_chunks, int chunk_elems, double m, void* stream);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,12 @@ class SimGeom(C.Structure):
                 ("d", C.c_int), ("b_off", C.c_int)]
 
 
+class OptimTensor(C.Structure):
+    """struct tan_optim_tensor (include/tan_b200.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("ema", C.c_void_p), ("numel", C.c_int64), ("decay", C.c_float), ("neg_step_size", C.c_float)]
+
+
 # symbol -> (restype, argtypes); every symbol include/tan_b200.h declares
 SIGNATURES = {
     "tan_abi_version": (C.c_int, []),
@@ -65,7 +71,7 @@ SIGNATURES = {
     "tan_layernorm": (C.c_int, [C.POINTER(LnArgs), C.c_void_p]),
     "tan_attention_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_void_p]),
+                                     C.c_void_p, C.c_void_p]),
     "tan_pos_from_time": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                     C.c_void_p]),
     "tan_sim_nce_workspace_bytes": (C.c_size_t, [C.POINTER(SimGeom)]),
@@ -114,6 +120,10 @@ SIGNATURES = {
     "tan_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tan_gemm_tn_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tan_optim_adamw_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tan_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
     "tan_attention_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 1
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const uint8_t* __restrict__ kpm, bf16* __restrict__ out,
-                 int64_t ldo, int Lq, int Lk, int tiles_per_cta) {
+                 int64_t ldo, int Lq, int Lk, int tiles_per_cta, float* __restrict__ lse, int lse_ld) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();     // the 128-byte swizzle atoms need 1024-byte aligned tiles
   uint8_t* sQ = smem;                               // [2][16 KB]
@@ -284,6 +284,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int gl = qt * nb + nb - 1;
       mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1);
       tc_fence_after();
+      // log2-domain log-sum-exp of the row's scaled scores for the backward pass (rows Lq .. lse_ld get +inf, so
+      // that exp2(s - lse) of a padding row is 0 there without a predicate)
+      if (lse != nullptr && q0 + row < lse_ld)
+        lse[(static_cast<int64_t>(b) * gridDim.x + h) * lse_ld + q0 + row] =
+            (live && q0 + row < Lq) ? m_ref + __log2f(l_run) : INFINITY;
       if (live) {
         float o[64];
         {
@@ -342,7 +347,7 @@ using namespace tanb;
 
 extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                   int64_t ldv, const uint8_t* key_padding_mask, void* out, int64_t ldo, int B, int H,
-                                  int Lq, int Lk, void* stream) {
+                                  int Lq, int Lk, float* lse, void* stream) {
   TAN_CHECK(tan_device_check());
   if (q == nullptr || k == nullptr || v == nullptr || out == nullptr)
     return set_error(TAN_ERR_ARG, "tan_attention_bf16: null pointer");
@@ -370,5 +375,6 @@ extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int
   const int tiles_per_cta = (nq_total + split - 1) / split;
   dim3 grid(H, B, (nq_total + tiles_per_cta - 1) / tiles_per_cta);
   return launch_pdl(attention_kernel, grid, dim3(kAttThreads), kAttSmem, static_cast<cudaStream_t>(stream), 1, tmQ,
-                    tmK, tmV, key_padding_mask, static_cast<bf16*>(out), ldo, Lq, Lk, tiles_per_cta);
+                    tmK, tmV, key_padding_mask, static_cast<bf16*>(out), ldo, Lq, Lk, tiles_per_cta, lse,
+                    (Lq + 63) / 64 * 64);
 }

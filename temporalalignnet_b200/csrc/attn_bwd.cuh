@@ -20,6 +20,9 @@ struct AttnBwdArgs {
   int B, H, Lq, Lk;
 };
 
+// attention_bwd_tc.cu: tcgen05 version (default); lse is an INPUT there (stored by the forward kernel, log2 domain,
+// pitch pad64(Lq)), delta a workspace of the same shape
+int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
 // attention_bwd.cu
 int attention_bwd_mma(const AttnBwdArgs& a, cudaStream_t stream);
 // attention_bwd_pipe.cu (experimental cp.async-pipelined variant, TAN_ATTN_BWD=pipe)

@@ -884,10 +884,12 @@ extern "C" int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k,
   a.dv = static_cast<bf16*>(dv); a.lddv = lddv;
   a.lse = lse; a.delta = delta;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
-  static const bool use_wmma = [] { const char* e = getenv("TAN_ATTN_BWD"); return e != nullptr && e[0] == 'w'; }();
-  // cp.async-pipelined mma.sync kernels by default (validated on B200 in round 2: 16.3 -> 12.1 ms per step at the
-  // bench shape); TAN_ATTN_BWD=mma selects the unpipelined ones, =wmma the first version
-  static const bool use_pipe = [] { const char* e = getenv("TAN_ATTN_BWD"); return e == nullptr || e[0] == 'p'; }();
+  // default: tcgen05 kernels (attention_bwd_tc.cu).  TAN_ATTN_BWD=pipe / mma / wmma select the legacy mma.sync /
+  // wmma versions (A/B aids; they recompute lse themselves and overwrite the buffer in their own layout)
+  static const char mode = [] { const char* e = getenv("TAN_ATTN_BWD"); return e == nullptr ? 't' : e[0]; }();
+  if (mode == 't') return attention_bwd_tc(a, static_cast<cudaStream_t>(stream));
+  static const bool use_wmma = mode == 'w';
+  static const bool use_pipe = mode == 'p';
   if (use_pipe && attention_bwd_pipe_supported(a)) return attention_bwd_mma_pipe(a, static_cast<cudaStream_t>(stream));
   if (!use_wmma) return attention_bwd_mma(a, static_cast<cudaStream_t>(stream));
   const int smem = static_cast<int>(sizeof(AttnBwdSmem)) + 128;

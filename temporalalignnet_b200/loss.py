@@ -13,6 +13,7 @@ with z = logits / 0.07, valid columns = real sentences, positives = same clip an
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -21,6 +22,11 @@ from torch.nn.utils.rnn import pad_sequence
 from . import ops
 from ._lib import TanError
 from .tan_model import LazyLogits
+
+
+# sharded mode: verify per call that all ranks pass the same (B_loc, N) (one 32-byte all-reduce on a side stream, no
+# main-stream synchronisation); TAN_SHARD_CHECK=0 skips it for loops whose shapes are fixed by construction
+SHARD_CHECK = os.environ.get("TAN_SHARD_CHECK", "1") != "0"
 
 
 def circulant(tensor, dim):
@@ -64,6 +70,52 @@ def _dist():
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None
+
+
+_shape_streams = {}
+
+
+def shard_shapes(B: int, N: int, device):
+    """(B_min, B_max, N_min, N_max) over the ranks of the default process group, exchanged on a SIDE stream: the host only
+    waits for a 32-byte all-reduce, not for the forward kernels already queued on the main stream."""
+    dist = _dist()
+    if dist is None:
+        return B, B, N, N
+    device = torch.device(device)
+    st = _shape_streams.get(str(device))
+    if st is None:
+        st = _shape_streams[str(device)] = torch.cuda.Stream(device=device) if device.type == "cuda" else False
+    v = torch.tensor([B, -B, N, -N], dtype=torch.int64)
+    if st:
+        with torch.cuda.stream(st):
+            t = v.to(device, non_blocking=True)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out = t.cpu()                      # synchronises the side stream only
+    else:                                      # gloo on CPU tensors (host tests)
+        t = v.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = t
+    return int(-out[1]), int(out[0]), int(-out[3]), int(out[2])
+
+
+def pad_text_to_global(lang_embed: torch.Tensor, lang_padding_mask: torch.Tensor):
+    """Sharded training with real data: every rank pads its batch to ITS OWN longest clip (`pad_sequence` in
+    data/loader_htm.py:111-129), so N differs between ranks, while the all-gathers of the sharded loss need one
+    N.  Call this on the text inputs BEFORE `model(...)` / `get_loss(...)`: pads to the longest N of any rank with
+    masked sentences (mask = 1, embedding = the clip's last row, as pad_sequence_by_last, data/loader_htm.py:13-23).
+    Returns (lang_embed, lang_padding_mask) unchanged when nothing needs padding."""
+    B, N = lang_embed.shape[0], lang_embed.shape[1]
+    b_min, b_max, _, n_max = shard_shapes(B, N, lang_embed.device)
+    if b_min != b_max:
+        raise TanError(f"sharded loss: every rank needs the same number of clips (this rank {B}, ranks have "
+                       f"{b_min}..{b_max}); use drop_last=True / a distributed sampler with equal shares")
+    if n_max == N:
+        return lang_embed, lang_padding_mask
+    pad = n_max - N
+    emb = torch.cat((lang_embed, lang_embed[:, -1:, :].expand(B, pad, lang_embed.shape[2])), dim=1).contiguous()
+    mask = torch.cat((lang_padding_mask, torch.ones(B, pad, dtype=lang_padding_mask.dtype,
+                                                    device=lang_padding_mask.device)), dim=1).contiguous()
+    return emb, mask
 
 
 class NceInputs:
@@ -324,6 +376,15 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     device = logits_dual.device
     shard = (_dist() is not None) if shard_batch is None else bool(shard_batch)
     dist = _dist() if shard else None
+    if dist is not None and SHARD_CHECK:
+        # the all-gathers below assume one (B_loc, N) on every rank; with real data N is each rank's own
+        # pad_sequence length -- fail loudly instead of hanging in NCCL or mis-indexing columns
+        b_min, b_max, n_min, n_max = shard_shapes(B, N, device)
+        if b_min != b_max or n_min != n_max:          # the same verdict on every rank: nobody enters a collective alone
+            raise TanError(f"sharded get_loss: ranks disagree on the batch shape (this rank B={B}, N={N}; ranks have "
+                           f"B {b_min}..{b_max}, N {n_min}..{n_max}).  Pad the text inputs with "
+                           "temporalalignnet_b200.loss.pad_text_to_global(lang_embed, lang_padding_mask) before the "
+                           "forward, and give every rank the same number of clips.")
     nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard)
     loss_dict = {}
     # training step: the forward ran with a tape (model.enable_autograd) -> the returned loss carries ONE autograd

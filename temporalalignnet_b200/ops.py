@@ -189,15 +189,16 @@ def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=Non
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kpm_u8: Optional[torch.Tensor],
-              out: torch.Tensor, B: int, H: int, Lq: int, Lk: int) -> None:
-    """tan_attention_bf16.  q/k/v/out are 2-D (possibly column-sliced) bf16 views [B*L, H*64]."""
+              out: torch.Tensor, B: int, H: int, Lq: int, Lk: int, lse: Optional[torch.Tensor] = None) -> None:
+    """tan_attention_bf16.  q/k/v/out are 2-D (possibly column-sliced) bf16 views [B*L, H*64]; lse (optional)
+    [B, H, pad64(Lq)] fp32 receives the rows' log2-domain log-sum-exp for the backward pass."""
     global _launches
     if _skip("attention", 4.0 * B * H * Lq * Lk * 64):
         return
     with _timed("attention", 4.0 * B * H * Lq * Lk * 64):
         check(lib().tan_attention_bf16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
                                        v.stride(0), _ptr(kpm_u8), out.data_ptr(), out.stride(0), B, H, Lq, Lk,
-                                       _stream()), "tan_attention_bf16")
+                                       _ptr(lse), _stream()), "tan_attention_bf16")
     _launches += 1
 
 
@@ -499,7 +500,8 @@ def sim_grad_gemm(a: torch.Tensor, t_pad: torch.Tensor, r0: int, g: SimGeom, pos
 
 
 def attention_bwd(q, k, v, o, d_out, kpm_u8, dq, dk, dv, lse, delta, B: int, H: int, Lq: int, Lk: int) -> None:
-    """tan_attention_bwd_bf16 (2-D, possibly column-sliced bf16 views as in `attention`)."""
+    """tan_attention_bwd_bf16 (2-D, possibly column-sliced bf16 views as in `attention`); lse [B, H, pad64(Lq)] is
+    what the forward `attention(..., lse=)` stored, delta a workspace of the same shape."""
     global _launches
     if _skip("attention_bwd", 10.0 * B * H * Lq * Lk * 64):
         return

@@ -616,18 +616,22 @@ class TwinTemporalAligner(nn.Module):
     def lang_model(self):
         return self.bert
 
+    @torch.no_grad()
     def _copy_param(self):
+        """model/tan_model.py:334-338.  In-place on the Parameters themselves (not on `.data`): the copy bumps
+        `_version`, which is what tells the target's bf16 weight shadows (tfm_model._Bf16Cache) to re-cast."""
         for po, pt in zip(self.online.parameters(), self.target.parameters()):
-            pt.data.copy_(po.data)
             pt.requires_grad = False
+            pt.copy_(po.detach())
 
     @torch.no_grad()
     def _momentum_update(self):
-        """model/tan_model.py:340-344, as one fused multi-tensor update instead of ~160 tiny kernels."""
-        po = [p.data for p in self.online.parameters()]
-        pt = [p.data for p in self.target.parameters()]
-        torch._foreach_mul_(pt, self.m)
-        torch._foreach_add_(pt, po, alpha=1.0 - self.m)
+        """model/tan_model.py:340-344 (p_t = m p_t + (1 - m) p_o) as ONE multi-tensor kernel launch
+        (tan_ema_update) instead of ~160 tiny kernels.  The target Parameters are updated in place THROUGH torch's
+        version counter (the reference reassigns `.data`; an update through `.data` would leave `_version` and the
+        pointer unchanged and the bf16 weight shadows the forward reads would silently stay at their old values)."""
+        from . import optim
+        optim.ema_update(list(self.target.parameters()), list(self.online.parameters()), self.m)
 
     def enable_cuda_graphs(self, enabled: bool = True) -> None:
         self.online.enable_cuda_graphs(enabled)

@@ -38,7 +38,7 @@ TN_GEMM = os.environ.get("TAN_TN_GEMM", "1") != "0"
 # tape
 # ------------------------------------------------------------------------------------------------------
 class LayerTape:
-    __slots__ = ("x_in", "xn", "qkv", "att", "x1", "xn2", "u", "h")
+    __slots__ = ("x_in", "xn", "qkv", "att", "lse", "x1", "xn2", "u", "h")
 
 
 class StackTape:
@@ -121,7 +121,9 @@ def run_encoder_stack_train(enc, x0: torch.Tensor, kpm, B: int, L: int, l_split:
         lt.qkv = torch.empty(M, 3 * d, **bf)
         ops.linear(lt.xn, cache.get(blk.attn.in_proj_weight), _f32(blk.attn.in_proj_bias), out_bf16=lt.qkv)
         lt.att = torch.empty(M, d, **bf)
-        ops.attention(lt.qkv[:, 0:d], lt.qkv[:, d:2 * d], lt.qkv[:, 2 * d:3 * d], kpm, lt.att, B, blk.n_head, L, L)
+        lt.lse = torch.empty(B, blk.n_head, ops.pad64(L), **f32)       # row statistics for the attention backward
+        ops.attention(lt.qkv[:, 0:d], lt.qkv[:, d:2 * d], lt.qkv[:, 2 * d:3 * d], kpm, lt.att, B, blk.n_head, L, L,
+                      lse=lt.lse)
         lt.x1 = torch.empty(M, d, **f32)
         ops.linear(lt.att, cache.get(blk.attn.out_proj.weight), _f32(blk.attn.out_proj.bias), residual=x, out_f32=lt.x1)
         lt.xn2 = torch.empty(M, d, **bf)
@@ -335,8 +337,7 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
     dy32 = torch.empty(M, d, **f32)
     datt = torch.empty(M, d, **bf)
     dqkv = torch.empty(M, 3 * d, **bf)
-    lse = torch.empty(B * blocks[0].n_head * L, **f32)
-    delta = torch.empty(B * blocks[0].n_head * L, **f32)
+    delta = torch.empty(B * blocks[0].n_head * ops.pad64(L), **f32)
     for i in range(S - 1, -1, -1):
         blk, lt = blocks[i], tape.layers[i]
         H = blk.n_head
@@ -354,7 +355,7 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
         _dgrad(dxb, ops.transpose_bf16(cache.get(blk.attn.out_proj.weight)), out_bf16=datt)
         _wgrad(dxb, lt.att, grads.of(blk.attn.out_proj.weight), grads.of(blk.attn.out_proj.bias))
         q, k, v = lt.qkv[:, 0:d], lt.qkv[:, d:2 * d], lt.qkv[:, 2 * d:3 * d]
-        ops.attention_bwd(q, k, v, lt.att, datt, tape.kpm, dqkv[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:3 * d], lse,
+        ops.attention_bwd(q, k, v, lt.att, datt, tape.kpm, dqkv[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:3 * d], lt.lse,
                           delta, B, H, L, L)
         sg = stage_grads[i - 1] if i >= 1 else None      # ln_1 of block i IS stage i-1 (model/tfm_model.py:50-53)
         _dgrad(dqkv, ops.transpose_bf16(cache.get(blk.attn.in_proj_weight)), out_f32=dy32, residual=sg)

@@ -87,8 +87,12 @@ def _scores(q, k, kpm, B, H, Lq, Lk):
     return s
 
 
-def attention(q, k, v, kpm_u8, out, B, H, Lq, Lk):
-    p = torch.softmax(_scores(q, k, kpm_u8, B, H, Lq, Lk), dim=-1)
+def attention(q, k, v, kpm_u8, out, B, H, Lq, Lk, lse=None):
+    s = _scores(q, k, kpm_u8, B, H, Lq, Lk)
+    p = torch.softmax(s, dim=-1)
+    if lse is not None:                                  # log2 domain, pitch pad64(Lq), +inf padding
+        lse.fill_(float("inf"))
+        lse.view(B, H, -1)[:, :, :Lq] = torch.logsumexp(s, -1) * 1.4426950408889634
     o = p @ _heads(v, B, Lk, H)
     out.copy_(o.permute(0, 2, 1, 3).reshape(B * Lq, H * 64).to(BF))
 
@@ -107,8 +111,7 @@ def attention_bwd(q, k, v, o, d_out, kpm_u8, dq, dk, dv, lse, delta, B, H, Lq, L
     dq.copy_(flat(ds @ _heads(k, B, Lk, H) * 0.125, Lq))
     dk.copy_(flat(ds.transpose(-1, -2) @ _heads(q, B, Lq, H) * 0.125, Lk))
     dv.copy_(flat(p.transpose(-1, -2) @ do, Lk))
-    lse.view(B, H, Lq).copy_(torch.logsumexp(s, -1))
-    delta.view(B, H, Lq).copy_(dl.squeeze(-1))
+    delta.view(B, H, -1)[:, :, :Lq] = dl.squeeze(-1)
 
 
 def quickgelu_fwd(u, h):
@@ -138,6 +141,13 @@ def transpose_bf16(x, out=None):
 def transpose_colsum_bf16(x, colsum_out, accumulate=True):
     colsum(x, colsum_out, accumulate)
     return transpose_bf16(x)
+
+
+def ema_update(target_params, online_params, m):
+    """Stand-in of optim.ema_update (tan_ema_update): in place on the Parameters, so version counters advance."""
+    with torch.no_grad():
+        for t, o in zip(target_params, online_params):
+            t.copy_(t * m + o.detach() * (1.0 - m))
 
 
 def gemm_tn(a, b, out, accumulate=True, tag="wgrad"):

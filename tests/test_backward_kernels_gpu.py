@@ -173,11 +173,16 @@ def test_attention_bwd(B, H, Lq, Lk, masked):
         return x2.float().view(B, L, H, 64).permute(0, 2, 1, 3)
 
     o_ref, dq_ref, dk_ref, dv_ref = _attn_ref(heads(q2, Lq), heads(k2, Lk), heads(v2, Lk), kpm, heads(dO2, Lq))
-    o2 = o_ref.permute(0, 2, 1, 3).reshape(B * Lq, d).to(torch.bfloat16).contiguous()
+    # the forward kernel provides o and the rows' log2-domain log-sum-exp ([B, H, pad64(Lq)], +inf padding)
+    Lp = ops.pad64(Lq)
+    o2 = torch.empty(B * Lq, d, dtype=torch.bfloat16, device=DEV)
+    lse = torch.full((B, H, Lp), 7.0, dtype=torch.float32, device=DEV)
+    ops.attention(q2, k2, v2, kpm, o2, B, H, Lq, Lk, lse=lse)
+    o_chk = o_ref.permute(0, 2, 1, 3).reshape(B * Lq, d)
+    assert ((o2.float() - o_chk).norm() / o_chk.norm()).item() < 1e-2
     dqkv = torch.zeros(B * Lq, d, dtype=torch.bfloat16, device=DEV)
     dkv = torch.zeros(B * Lk, 2 * d, dtype=torch.bfloat16, device=DEV)
-    lse = torch.empty(B, H, Lq, dtype=torch.float32, device=DEV)
-    delta = torch.empty(B, H, Lq, dtype=torch.float32, device=DEV)
+    delta = torch.empty(B, H, Lp, dtype=torch.float32, device=DEV)
     ops.attention_bwd(q2, k2, v2, o2, dO2, kpm, dqkv, dkv[:, :d], dkv[:, d:], lse, delta, B, H, Lq, Lk)
     torch.cuda.synchronize()
 
@@ -187,7 +192,10 @@ def test_attention_bwd(B, H, Lq, Lk, masked):
     s = (heads(q2, Lq) @ heads(k2, Lk).transpose(-1, -2)) * 0.125
     if kpm is not None:
         s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
-    assert (lse - torch.logsumexp(s, -1)).abs().max().item() < 1e-3
+    assert (lse[:, :, :Lq] * 0.6931471805599453 - torch.logsumexp(s, -1)).abs().max().item() < 2e-3
+    assert torch.isinf(lse[:, :, Lq:]).all() and (lse[:, :, Lq:] > 0).all()
+    d_ref = (heads(dO2, Lq) * heads(o2, Lq)).sum(-1)
+    assert (delta[:, :, :Lq] - d_ref).abs().max().item() < 1e-2 and (delta[:, :, Lq:] == 0).all()
     for got, ref, L in ((dqkv, dq_ref, Lq), (dkv[:, :d], dk_ref, Lk), (dkv[:, d:], dv_ref, Lk)):
         ref2 = flat(ref, L)
         err = ((got.float() - ref2).norm() / ref2.norm()).item()

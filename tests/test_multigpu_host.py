@@ -186,8 +186,10 @@ def test_circulant_known_answer():
     assert circulant(torch.tensor([0, 1, 2]), dim=0).tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
 
 
-def test_state_dict_keys_match_reference_names():
-    from temporalalignnet_b200 import TemporalAligner, TwinTemporalAligner
+def test_state_dict_keys_match_reference_names(monkeypatch):
+    from temporalalignnet_b200 import TemporalAligner, TwinTemporalAligner, optim
+    from tests import cpu_ops
+    monkeypatch.setattr(optim, "ema_update", cpu_ops.ema_update)      # the product's EMA update is a CUDA kernel
     m = TemporalAligner(2, 3, random_pos_start=0, use_alignability_head=1)
     ref_keys = set(synth.make_state_dict(2, 3, use_alignability_head=True))
     assert set(m.state_dict().keys()) == ref_keys
@@ -197,9 +199,17 @@ def test_state_dict_keys_match_reference_names():
     p0 = [p.clone() for p in tw.target.parameters()]
     for p in tw.online.parameters():
         p.data.add_(1.0)
+    v0 = [p._version for p in tw.target.parameters()]
     tw._momentum_update()
     for a, b, o in zip(p0, tw.target.parameters(), tw.online.parameters()):
         assert torch.allclose(b, a * 0.99 + o * 0.01, atol=1e-6)
+    # the bf16 weight shadows of the target watch the version counters (tfm_model._Bf16Cache): every update
+    # must advance them, and so must _copy_param
+    assert all(p._version > v for p, v in zip(tw.target.parameters(), v0))
+    v1 = [p._version for p in tw.target.parameters()]
+    tw._copy_param()
+    assert all(p._version > v for p, v in zip(tw.target.parameters(), v1))
+    assert all(torch.equal(a, b) for a, b in zip(tw.target.parameters(), tw.online.parameters()))
 
 
 def _train_worker(rank, world, port, ret):
@@ -259,3 +269,53 @@ def test_two_rank_sharded_training_step_equals_single_process():
         assert same_keys
         assert loss_err < 2e-4, loss_err
         assert grad_err < 2e-2, grad_err
+
+
+def _shape_worker(rank, world, port, ret):
+    """Ranks with different local N (each rank's own pad_sequence length, as with real data): get_loss must refuse
+    with a clear error, pad_text_to_global must bring every rank to the longest N."""
+    import types
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from temporalalignnet_b200 import TanError
+    from temporalalignnet_b200 import loss as L
+    B, T, N = 2, 16, 3 + rank                                  # rank 1 has one more sentence column
+    assert L.shard_shapes(B, N, "cpu") == (2, 2, 3, 4)
+    text = torch.randn(B, N, 8)
+    tpm = torch.zeros(B, N, dtype=torch.bool)
+    tpm[1, -1] = True
+    emb2, mask2 = L.pad_text_to_global(text, tpm)
+    ok = tuple(emb2.shape) == (B, 4, 8) and tuple(mask2.shape) == (B, 4)
+    if rank == 0:
+        ok = ok and bool(mask2[:, 3].all()) and torch.equal(emb2[:, 3], text[:, 2]) and torch.equal(emb2[:, :3], text)
+    else:
+        ok = ok and emb2 is text and mask2 is tpm
+    # get_loss on the unpadded, disagreeing shapes refuses before any collective of mismatched size
+    args = types.SimpleNamespace(model="init", sim="cos", learn_agreement=0, loss_threshold=0.0, use_alignability_head=0)
+    lg = torch.zeros(B, 1, T, B, N)
+    err = ""
+    try:
+        L.get_loss({"start": [[0.0]] * B, "end": [[1.0]] * B, "text": None}, torch.zeros(B, T, 4), text, None, tpm,
+                   {"logits_dual": lg, "logits_joint": lg}, args, None)
+    except TanError as e:
+        err = str(e)
+    # different clip counts are an error of their own
+    err_b = ""
+    try:
+        L.pad_text_to_global(torch.randn(B + rank, 4, 8), torch.zeros(B + rank, 4, dtype=torch.bool))
+    except TanError as e:
+        err_b = str(e)
+    res = [None] * world
+    dist.all_gather_object(res, (ok, "pad_text_to_global" in err, "same number of clips" in err_b))
+    if rank == 0:
+        ret["res"] = res
+    dist.destroy_process_group()
+
+
+def test_sharded_shape_disagreement_is_detected_and_padding_helper_fixes_it():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_shape_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(all(r) for r in ret["res"]), ret["res"]
