@@ -229,6 +229,69 @@ def run_param_grads():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "g_param_grads.npz"), **out)
 
 
+# Reference-generated fixtures at the BENCHMARKED shapes (parity must not stop at T = 160):
+#   c3: BASELINE configs[2]'s per-clip shape (E6D6, T=256, N=32) at 4 clips, `--model init` loss
+#   c5: BASELINE configs[4]'s loss recipe (learn_agreement + loss_threshold + alignability head, train/loss.py:88-357)
+#       at T=512, N=64 with a joint stack deep enough for the head (D=3)
+BENCH_CASES = {
+    "c3": dict(E=6, D=6, B=4, T=256, N=32, pad_video_every=0, use_text_pos_enc=0, head=0, seed=31, kw={}),
+    "c5": dict(E=2, D=3, B=4, T=512, N=64, pad_video_every=0, use_text_pos_enc=0, head=1, seed=32,
+               kw=dict(learn_agreement=1, loss_threshold=0.5, use_alignability_head=1)),
+}
+
+
+def run_bench_cases():
+    """Forward + get_loss + autograd of the UNMODIFIED reference at the benchmarked shapes -> g_bench.npz: the loss
+    dict, a strided subsample of the logits, and per parameter the gradient norm + a strided subsample."""
+    tfm, tan, ref_loss = load_reference()
+    out = {}
+    for tag, c in BENCH_CASES.items():
+        m, sd = build_reference_model(tan, c["E"], c["D"], c["use_text_pos_enc"], c["head"], seed=c["seed"])
+        m.train()
+        batch = synth.make_batch(c["B"], c["T"], c["N"], pad_video_every=c["pad_video_every"], seed=c["seed"],
+                                 force_full=True)
+        video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+        vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+        res = m(video, text, vpm, tpm, None)
+        input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
+        # get_loss fills the logits in place under learn_agreement (train/loss.py:96-100): keep pristine copies
+        for k in ("logits_dual", "logits_joint"):
+            out[f"{tag}/{k}_sub"] = res[k].detach()[:, :, ::16].numpy().copy()
+        loss = ref_loss.get_loss(input_data, video, text, vpm.float(), tpm.float(), res, loss_args(**c["kw"]), None)
+        loss["loss"].backward()
+        for k, v in loss.items():
+            out[f"{tag}/loss/{k}"] = np.array(float(v))
+        out[f"{tag}/in_checksum"] = np.array(checksum(batch["video"]) + checksum(batch["text"]) +
+                                             sum(checksum(v) for v in sd.values()))
+        for name, p in m.named_parameters():
+            if name.startswith("bert.") or p.grad is None:
+                continue
+            g = p.grad.detach().double().reshape(-1)
+            out[f"{tag}/norm/{name}"] = np.array(float(g.norm()))
+            out[f"{tag}/sub/{name}"] = g[::GRAD_STRIDE].float().numpy()
+        print("bench case", tag, {k: round(float(v), 6) for k, v in loss.items()})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_bench.npz"), **out)
+
+
+def run_align():
+    """get_alignability (model/tan_model.py:284-312) of the reference for the head-carrying case g2, without and with
+    positional interpolation (tuple form: video table, text table) -> g_align.npz."""
+    tfm, tan, ref_loss = load_reference()
+    cfg = CASES["g2_e2d3_T24_B3"]
+    m, sd = build_reference_model(tan, cfg["E"], cfg["D"], cfg["use_text_pos_enc"], 1)
+    batch = synth.make_batch(cfg["B"], cfg["T"], cfg["N"], pad_video_every=cfg["pad_video_every"])
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    out = {}
+    with torch.no_grad():
+        a = m.get_alignability(video, text)
+        b = m.get_alignability(video, text, (12, 3))
+    for k in a:
+        out[k] = a[k].numpy()
+        out[k + "/interp_12_3"] = b[k].numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_align.npz"), **out)
+    print("g_align", {k: v.shape for k, v in out.items()})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -247,6 +310,10 @@ def main():
         run_loss_cases()
     if not a.only or a.only == "g_param_grads":
         run_param_grads()
+    if not a.only or a.only == "g_bench":
+        run_bench_cases()
+    if not a.only or a.only == "g_align":
+        run_align()
 
 
 if __name__ == "__main__":

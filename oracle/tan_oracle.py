@@ -245,6 +245,22 @@ class TanOracle:
         return torch.einsum("bstc,bskc->bstk", jvn, jtn)
 
 
+    def get_alignability(self, video, text, interpolate_from=None, pos_starts=(0, 0)):
+        """model/tan_model.py:284-312 -> {'alignability-dual' [B,N,1], 'alignability-joint' [B,S,N,1]}: binary_head
+        on the raw text features and on every stage of the joint stack's text part (zero padding masks)."""
+        t_if = None
+        if isinstance(interpolate_from, (list, tuple)):
+            interpolate_from, t_if = interpolate_from
+        t_raw = self.get_textual_feature(text)
+        t = (self.get_textual_feature_with_time(text, t_if, pos_starts[0]) if self.use_text_pos_enc else t_raw)
+        B, T, _ = video.shape
+        N = t.shape[1]
+        _, jt = self.get_joint_feature(video, torch.zeros(B, T, dtype=torch.bool), t,
+                                       torch.zeros(B, N, dtype=torch.bool), interpolate_from, pos_starts[1])
+        w, b = self.sd["binary_head.weight"], self.sd["binary_head.bias"]
+        return {"alignability-dual": t_raw @ w.t() + b, "alignability-joint": jt @ w.t() + b}
+
+
 # ------------------------------------------------------------------------------------------------
 # Loss (train/loss.py)
 # ------------------------------------------------------------------------------------------------

@@ -27,7 +27,12 @@ from ._lib import ACT_NONE, TanError
 from .tfm_model import StageSink, _f32, _mask_u8
 
 AUTOGRAD_DEFAULT = os.environ.get("TAN_AUTOGRAD", "0") != "0"
-SIM_BWD_ROWS = 8192          # rows of one similarity-gradient chunk (z chunk = rows x C fp32)
+# rows of one similarity-gradient chunk (G = rows x C bf16).  Measured on B200 at the bench shape (R = 65 536 rows,
+# C = 8192): 29.1 / 20.9 / 18.8 / 16.6 ms of similarity-backward GEMMs per step at 4096 / 8192 / 16384 / 65536 rows --
+# a chunk's dA / dB products have only 64 output tiles for 74 CTA pairs, larger chunks amortise that; G is capped
+# at SIM_BWD_G_BYTES
+SIM_BWD_ROWS = int(os.environ.get("TAN_SIM_BWD_ROWS", "65536"))
+SIM_BWD_G_BYTES = 2 << 30
 SIM_GRAD_FUSED = os.environ.get("TAN_SIM_GRAD_FUSED", "1") != "0"     # G in the epilogue of the recomputation GEMM
 SIM_GRAD_GT = os.environ.get("TAN_SIM_GRAD_GT", "0") == "1"           # experimental: G^T from the same epilogue
 # weight gradients / the text-side similarity gradient on MN-major operands (tan_gemm_tn_bf16): no transposes
@@ -428,7 +433,7 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
     ra, rap, cb, cbp = sim_coefficients(ctx, scale, dist)
     vsm = vfeat.permute(1, 0, 2, 3).reshape(S, B * T, d).contiguous()         # stage-major rows
     R = B * T
-    Rc = min(R, SIM_BWD_ROWS)
+    Rc = min(R, SIM_BWD_ROWS, max(256, (SIM_BWD_G_BYTES // (2 * Cp)) // 256 * 256))
     g = ops.sim_geom(B, 1, T, C, nce.N, d, nce.b_off)
     fused = SIM_GRAD_FUSED and nce.N <= 64
     z = None if fused else torch.empty(Rc, Cp, dtype=torch.float32, device=dev)

@@ -123,3 +123,50 @@ def compare_param_grads(model, ref_grads, loose=False):
         if not (cos >= tol_cos and rel <= tol_rel):
             bad.append((name, round(cos, 5), round(rel, 4)))
     assert not bad, bad
+
+
+# must mirror oracle/make_golden.py:BENCH_CASES (reference-generated fixtures at the benchmarked shapes)
+BENCH_CASES = {
+    "c3": dict(E=6, D=6, B=4, T=256, N=32, pad_video_every=0, use_text_pos_enc=0, head=0, seed=31, kw={}),
+    "c5": dict(E=2, D=3, B=4, T=512, N=64, pad_video_every=0, use_text_pos_enc=0, head=1, seed=32,
+               kw=dict(learn_agreement=1, loss_threshold=0.5, use_alignability_head=1)),
+}
+
+
+def bench_case_inputs(tag):
+    """(cfg, state_dict, batch, loss-args namespace, fixture) of a g_bench.npz case, regenerated from seeds."""
+    import types
+    c = BENCH_CASES[tag]
+    g = load_golden("g_bench")
+    sd = synth.make_state_dict(c["E"], c["D"], use_alignability_head=bool(c["head"]), seed=c["seed"])
+    batch = synth.make_batch(c["B"], c["T"], c["N"], pad_video_every=c["pad_video_every"], seed=c["seed"],
+                             force_full=True)
+    chk = checksum(batch["video"]) + checksum(batch["text"]) + sum(checksum(v) for v in sd.values())
+    assert abs(chk - float(g[f"{tag}/in_checksum"])) < 1e-6 * abs(chk), "synthetic RNG drifted"
+    a = dict(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep", loss_threshold=0.0,
+             use_alignability_head=0, optim_policy="default")
+    a.update(c["kw"])
+    return c, sd, batch, types.SimpleNamespace(**a), g
+
+
+def compare_grads_to_fixture(named_grads, g, tag, tol_norm, tol_cos):
+    """Gradients against the reference's per-parameter norm + every-997th-element subsample (g_bench / g_param_grads
+    layout).  named_grads: {name: tensor or None}."""
+    names = [k[len(tag) + 6:] for k in g if k.startswith(f"{tag}/norm/")]
+    assert len(names) >= 37
+    bad = []
+    for name in names:
+        gr = named_grads.get(name)
+        assert gr is not None, f"no gradient for {name}"
+        got = gr.detach().double().cpu().reshape(-1)
+        ref_norm = float(g[f"{tag}/norm/{name}"])
+        sub = torch.from_numpy(g[f"{tag}/sub/{name}"]).double()
+        if ref_norm == 0.0:
+            assert float(got.norm()) == 0.0, name
+            continue
+        rel = abs(float(got.norm()) - ref_norm) / ref_norm
+        gs = got[::997]
+        cos = float((gs @ sub) / (gs.norm() * sub.norm()).clamp_min(1e-300)) if sub.numel() >= 64 else 1.0
+        if rel > tol_norm or cos < tol_cos:
+            bad.append((name, round(rel, 4), round(cos, 5)))
+    assert not bad, bad

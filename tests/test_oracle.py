@@ -224,3 +224,62 @@ def test_oracle_param_grads_vs_reference_fixture(tag):
     for name, gr in grads.items():
         if name not in names:
             assert gr is None or float(gr.abs().max()) == 0.0, name
+
+
+@pytest.mark.parametrize("tag", ["c3", "c5"])
+def test_oracle_at_benchmarked_shapes_vs_reference_fixture(tag):
+    """g_bench.npz: forward + get_loss + autograd of the UNMODIFIED reference at BASELINE configs[2]'s per-clip shape
+    (E6D6, T=256, N=32) and with configs[4]'s loss recipe at T=512, N=64 (oracle/make_golden.py:run_bench_cases)."""
+    from tests.helpers import bench_case_inputs, compare_grads_to_fixture, oracle_param_grads
+    c, sd, batch, args, g = bench_case_inputs(tag)
+    orc = O.TanOracle(sd, c["E"], c["D"], use_alignability_head=c["head"])
+    with torch.no_grad():
+        out = orc.forward(torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"]),
+                          batch["video_padding_mask"], batch["text_padding_mask"])
+    for k in ("logits_dual", "logits_joint"):
+        assert max_abs(out[k][:, :, ::16], g[f"{tag}/{k}_sub"]) < FP32_TOL
+    loss, grads = oracle_param_grads(c, sd, batch, args)
+    assert abs(loss - float(g[f"{tag}/loss/loss"])) < 2e-5 * abs(loss)
+    compare_grads_to_fixture(grads, g, tag, tol_norm=5e-4, tol_cos=0.99999)
+
+
+def test_oracle_get_alignability_vs_reference_fixture():
+    g = load_golden("g_align")
+    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
+    orc = O.TanOracle(sd, cfg["E"], cfg["D"], use_text_pos_enc=1, use_alignability_head=1)
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    a = orc.get_alignability(video, text)
+    b = orc.get_alignability(video, text, (12, 3))
+    for k in ("alignability-dual", "alignability-joint"):
+        assert max_abs(a[k], g[k]) < 1e-4
+        assert max_abs(b[k], g[k + "/interp_12_3"]) < 1e-4
+
+
+def test_sine_position_table_vs_reference_fixture():
+    """model/tfm_model.py:137-148 (host-side constant of the product)."""
+    from temporalalignnet_b200.tfm_model import get_position_embedding_sine
+    g = load_golden("g_blocks")
+    assert np.array_equal(get_position_embedding_sine(8, 16).numpy(), g["sine_pos_16x8"])
+
+
+def test_eager_port_matches_oracle_on_cpu():
+    """oracle/eager_port.py (the torch-eager baseline bench.py times on the GPU: nn.MultiheadAttention, boolean-index
+    loss) computes the same forward + loss as the oracle on the same weights (fp32, CPU)."""
+    from oracle import eager_port as EP
+    E, D, B, T, N = 2, 2, 3, 24, 5
+    sd = synth.make_state_dict(E, D, seed=9)
+    batch = synth.make_batch(B, T, N, seed=9, pad_video_every=2, force_full=True)
+    m = EP.EagerTAN(E, D)
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    video, text = torch.from_numpy(batch["video"]), torch.from_numpy(batch["text"])
+    vpm, tpm = torch.from_numpy(batch["video_padding_mask"]), torch.from_numpy(batch["text_padding_mask"])
+    with torch.no_grad():
+        out = m(video, text, vpm, tpm)
+        loss = EP.eager_get_loss_init(out, batch["start"], batch["end"], tpm, T, N)
+        ref = O.TanOracle(sd, E, D).forward(video, text, batch["video_padding_mask"], batch["text_padding_mask"])
+        ref_loss = O.get_loss_init(ref["logits_dual"], ref["logits_joint"], batch["start"], batch["end"],
+                                   batch["text_padding_mask"])
+    assert max_abs(out["logits_dual"], ref["logits_dual"]) < FP32_TOL
+    assert max_abs(out["logits_joint"], ref["logits_joint"]) < FP32_TOL
+    for k in ("loss", "loss-dual", "loss-joint"):
+        assert abs(float(loss[k]) - float(ref_loss[k])) < 1e-5 * abs(float(ref_loss[k])), k
