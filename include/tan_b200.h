@@ -335,28 +335,11 @@ TAN_API int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pad, 
  * d loss / d cos of rows r0 .. r0+Rc of one stage, computed in the epilogue of the tcgen05 pair GEMM
  * <vfeat[r], tfeat[c]> (vfeat [Rc, d] bf16 (ldv), tfeat [C_pad, d] bf16 (ldt), rows beyond g->C zero) -- the
  * fp32 cosines never reach HBM.  Same coefficient vectors / targets as tan_sim_grad_tiles; g->N <= 64,
- * C_pad % 128 == 0, d % 64 == 0.  The transposed operand of dB is made with tan_transpose_bf16. */
+ * C_pad % 128 == 0, d % 64 == 0.  dB = G^T @ vfeat then runs on tan_gemm_tn_bf16 straight from G (no transpose). */
 TAN_API int tan_sim_grad_gemm(const void* vfeat, int64_t ldv, const void* tfeat, int64_t ldt, int Rc, int r0,
                               const tan_sim_geom* g, int C_pad, const uint32_t* posbits, const uint8_t* col_valid,
                               const uint8_t* row_kill, const float* ra, const float* rap, const float* cb,
                               const float* cbp, void* G, int64_t ldg, void* stream);
-
-/* EXPERIMENTAL (round 1: compiled, not yet run on a GPU; train.py uses it only with TAN_SIM_GRAD_GT=1):
- * tan_sim_grad_gemm that also writes GT [C_pad, ldgt] = G^T from the epilogue (rows Rc .. Rc_pad zero), which makes
- * the tan_transpose_bf16 pass over G unnecessary. */
-TAN_API int tan_sim_grad_gemm_gt(const void* vfeat, int64_t ldv, const void* tfeat, int64_t ldt, int Rc, int r0,
-                                 const tan_sim_geom* g, int C_pad, const uint32_t* posbits, const uint8_t* col_valid,
-                                 const uint8_t* row_kill, const float* ra, const float* rap, const float* cb,
-                                 const float* cbp, void* G, int64_t ldg, void* GT, int64_t ldgt, int Rc_pad,
-                                 void* stream);
-
-/* EXPERIMENTAL (round 1: compiled, not yet run on a GPU; train.py uses it only with TAN_FUSE_BIAS_SUM=1):
- * tan_transpose_bf16 that also produces colsum[c] (+)= sum_r in[r, c] -- the bias gradient of the dY whose transpose
- * feeds the weight-gradient GEMM -- in the same pass (deterministic per-tile partials through `workspace`). */
-TAN_API size_t tan_transpose_colsum_workspace_bytes(int R, int C);
-TAN_API int tan_transpose_colsum_bf16(const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int R_pad,
-                                      float* colsum, int accumulate, void* workspace, size_t workspace_bytes,
-                                      void* stream);
 
 /* out[P, Q] (+)= A[R, P]^T @ B[R, Q]: bf16 row-major operands consumed as they lie in HBM (MN-major UMMA operands,
  * no transposes), the contraction running over their R rows; fp32 accumulation and output (row pitch ldo; added to
@@ -379,6 +362,29 @@ TAN_API int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, in
                                    const uint8_t* key_padding_mask, void* dq, int64_t lddq, void* dk, int64_t lddk,
                                    void* dv, int64_t lddv, float* lse, float* delta, int B, int H, int Lq, int Lk,
                                    void* stream);
+
+/* ---- text embedder (model/word2vec_model.py:76-102) ----------------------------- */
+
+/* out[r, :] = table[ids[r], :] for r < n: rows of the (frozen) bf16 embedding table [V, ld] (nn.Embedding lookup at
+ * model/word2vec_model.py:84-85; ld = 320 = the 300 word2vec dimensions zero-padded to a multiple of 64 so that the
+ * result is the K-major A operand of fc1).  ids outside [0, V) read row 0 (the padding / unknown word). */
+TAN_API int tan_embed_gather_bf16(const int64_t* ids, const void* table, int64_t ld, int V, int64_t n, void* out,
+                                  void* stream);
+
+/* pooled[s, f] = max over the 32 words w of sentence s of  keep(s, w) ? relu(x[s*32 + w, :] . w1[f, :] + b1[f]) : -6e4
+ * (model/word2vec_model.py:86,:92-96): the fc1 GEMM on tcgen05 with bias + ReLU + masked max-pool fused into its
+ * epilogue (an epilogue warp's 32 TMEM lanes are one sentence).  x [S*32, K] bf16 (ldx), w1 [F, K] bf16 (ldw),
+ * b1 [F] fp32 or NULL, keep [S*32] uint8 attention mask (1 = keep) or NULL; a sentence whose words are all ignored
+ * keeps all of them (:93).  pooled [S, F] bf16; argmax [S, F] uint8 (optional): the first word attaining the maximum,
+ * for tan_text_pool_bwd.  F % 128 == 0, K % 64 == 0. */
+TAN_API int tan_text_pool_fc1(const void* x, int64_t ldx, const void* w1, int64_t ldw, const float* b1,
+                              const uint8_t* keep, int S, int F, int K, void* pooled, uint8_t* argmax, void* stream);
+
+/* Backward of the pooling + ReLU: dH[s*32 + w, f] = (w == argmax[s, f] && pooled[s, f] > 0) ? dpool[s, f] : 0
+ * (bf16 [S*32, F]), the operand of dW1 = dH^T x (tan_gemm_tn_bf16) and db1 (tan_colsum).  Autograd of
+ * torch.max / F.relu at model/word2vec_model.py:86,:95. */
+TAN_API int tan_text_pool_bwd(const void* dpool, const void* pooled, const uint8_t* argmax, int S, int F, void* dH,
+                              void* stream);
 
 /* ---- optimizer step (co-training step) ------------------------------------------ */
 

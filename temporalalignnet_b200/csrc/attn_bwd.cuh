@@ -1,5 +1,4 @@
-// Shared argument block of the attention backward implementations (backward.cu: wmma reference version,
-// attention_bwd.cu: register-resident mma.sync version).
+// Argument block of the attention backward (entry point in backward.cu, kernels in attention_bwd_tc.cu).
 #pragma once
 #include "common.cuh"
 
@@ -20,13 +19,8 @@ struct AttnBwdArgs {
   int B, H, Lq, Lk;
 };
 
-// attention_bwd_tc.cu: tcgen05 version (default); lse is an INPUT there (stored by the forward kernel, log2 domain,
-// pitch pad64(Lq)), delta a workspace of the same shape
+// attention_bwd_tc.cu: tcgen05 kernels; lse is an INPUT (stored by the forward kernel, log2 domain, pitch pad64(Lq)),
+// delta a workspace of the same shape
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t stream);
-// attention_bwd.cu
-int attention_bwd_mma(const AttnBwdArgs& a, cudaStream_t stream);
-// attention_bwd_pipe.cu (experimental cp.async-pipelined variant, TAN_ATTN_BWD=pipe)
-bool attention_bwd_pipe_supported(const AttnBwdArgs& a);
-int attention_bwd_mma_pipe(const AttnBwdArgs& a, cudaStream_t stream);
 
 }  // namespace tanb

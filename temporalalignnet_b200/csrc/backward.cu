@@ -1,16 +1,9 @@
-// Backward-pass kernels of the TAN hot path (training step): everything that is NOT a plain GEMM.
-// The GEMM-shaped part of the backward pass (dgrad = dY @ W, wgrad = dY^T @ X, the similarity-matrix
-// recomputation and its two gradient products) runs on the tcgen05 pair GEMM of gemm_linear.cu through
-// tan_linear_bf16 with transposed operands; this file provides the operand transposes, the bias / LayerNorm
-// parameter reductions, QuickGELU, LayerNorm, L2-normalisation, the similarity-gradient tile kernel and the
-// attention backward kernels.
-//
-// Status (round 1): first correct path.  The attention backward uses the legacy warp-level tensor path
-// (mma.sync through nvcuda::wmma) and recomputes the score tiles in two kernels (dQ + softmax statistics,
-// then dK / dV) so that no atomics are needed and the result is deterministic; a tcgen05 version with the
-// accumulators in TMEM is the follow-up.
-#include <mma.h>
-
+// Backward-pass kernels of the TAN hot path (training step): everything that is NOT a GEMM or attention.
+// The GEMM-shaped part of the backward pass runs on the tcgen05 pair GEMMs (dgrad = dY @ W and the similarity
+// recomputation: tan_linear_bf16 / tan_sim_grad_gemm; wgrad = dY^T @ X and dB = G^T V: tan_gemm_tn_bf16 on
+// MN-major operands), the attention backward in attention_bwd_tc.cu (tcgen05); this file provides the bf16
+// transpose (weight shadows), the bias / LayerNorm parameter reductions, QuickGELU, LayerNorm, L2-normalisation,
+// the similarity-gradient tile kernel (N > 64) and the entry point of the attention backward.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -390,270 +383,6 @@ __global__ void __launch_bounds__(256) sim_grad_kernel(const float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Attention backward (head_dim 64), per (clip b, head h).  With s_ij = q_i . k_j / 8 + mask_j,
-// p_ij = softmax_j s_ij, o_i = sum_j p_ij v_j and the incoming gradient do_i:
-//   delta_i = <do_i, o_i>,  dp_ij = <do_i, v_j>,  ds_ij = p_ij (dp_ij - delta_i)
-//   dq_i = sum_j ds_ij k_j / 8,   dk_j = sum_i ds_ij q_i / 8,   dv_j = sum_i p_ij do_i.
-// Kernel A (CTA = 64 queries): pass 1 recomputes the scores to get lse_i, pass 2 accumulates dq; writes lse and
-// delta.  Kernel B (CTA = 64 keys): walks the query blocks and accumulates dk, dv.  bf16 operands, fp32
-// accumulation (wmma m16n16k16), 4 warps: warp w owns 16 of the CTA's 64 rows.
-// ------------------------------------------------------------------------------------------------
-namespace wm = nvcuda::wmma;
-constexpr int kAB = 64;          // block edge (queries / keys per CTA step)
-constexpr int kAP = 72;          // bf16 smem row pitch (elements)
-constexpr int kAF = 68;          // fp32 smem row pitch (elements)
-constexpr float kAttScale = 0.125f;
-
-struct AttnBwdSmem {
-  bf16 q[kAB][kAP];
-  bf16 dO[kAB][kAP];
-  bf16 k[kAB][kAP];
-  bf16 v[kAB][kAP];
-  bf16 p[kAB][kAP];
-  bf16 ds[kAB][kAP];
-  float s[kAB][kAF];
-  float dp[kAB][kAF];
-  float lse[kAB];
-  float delta[kAB];
-  float bias[kAB];       // 0 or -inf per key of the current block
-};
-
-// rows [row0, row0 + 64) x 64 columns of a [*, ld] bf16 matrix (columns col0..col0+63) -> smem, zero beyond n_rows
-__device__ __forceinline__ void attn_load_block(bf16 (*dst)[kAP], const bf16* src, int64_t ld, int row0, int n_rows,
-                                                int64_t base_row, int col0) {
-  for (int i = threadIdx.x; i < kAB * 8; i += blockDim.x) {
-    const int r = i >> 3, c8 = (i & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row0 + r < n_rows) v = *reinterpret_cast<const uint4*>(src + (base_row + row0 + r) * ld + col0 + c8);
-    *reinterpret_cast<uint4*>(&dst[r][c8]) = v;
-  }
-}
-
-// acc[16 x 64] (4 n-tiles) (+)= A_w[16 x 64] (row-major in smem) @ B^T where B is [64 n][64 k] row-major (i.e. col_major B)
-__device__ __forceinline__ void mm_a_bt(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], const bf16* a_rows,
-                                        const bf16 (*bmat)[kAP]) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::row_major> fa;
-    wm::load_matrix_sync(fa, a_rows + kk * 16, kAP);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::col_major> fb;
-      wm::load_matrix_sync(fb, &bmat[j * 16][kk * 16], kAP);
-      wm::mma_sync(acc[j], fa, fb, acc[j]);
-    }
-  }
-}
-
-// acc[16 x 64] += A_w[16 x 64] (row-major) @ B where B is [64 k][64 n] row-major
-__device__ __forceinline__ void mm_a_b(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], const bf16* a_rows,
-                                       const bf16 (*bmat)[kAP]) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::row_major> fa;
-    wm::load_matrix_sync(fa, a_rows + kk * 16, kAP);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::row_major> fb;
-      wm::load_matrix_sync(fb, &bmat[kk * 16][j * 16], kAP);
-      wm::mma_sync(acc[j], fa, fb, acc[j]);
-    }
-  }
-}
-
-// acc[16 x 64] += A^T_w @ B: A is [64 k][64 m] row-major in smem, this warp takes columns m0..m0+15 of it
-__device__ __forceinline__ void mm_at_b(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4],
-                                        const bf16 (*amat)[kAP], int m0, const bf16 (*bmat)[kAP]) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    wm::fragment<wm::matrix_a, 16, 16, 16, bf16, wm::col_major> fa;
-    wm::load_matrix_sync(fa, &amat[kk * 16][m0], kAP);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      wm::fragment<wm::matrix_b, 16, 16, 16, bf16, wm::row_major> fb;
-      wm::load_matrix_sync(fb, &bmat[kk * 16][j * 16], kAP);
-      wm::mma_sync(acc[j], fa, fb, acc[j]);
-    }
-  }
-}
-
-__device__ __forceinline__ void acc_zero(wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) wm::fill_fragment(acc[j], 0.f);
-}
-
-__device__ __forceinline__ void acc_store(const wm::fragment<wm::accumulator, 16, 16, 16, float> (&acc)[4], float* rows) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) wm::store_matrix_sync(rows + j * 16, acc[j], kAF, wm::mem_row_major);
-}
-
-
-__device__ __forceinline__ void attn_fill_bias(float* bias, const uint8_t* kpm, int b, int Lk, int k0) {
-  for (int j = threadIdx.x; j < kAB; j += blockDim.x) {
-    const int key = k0 + j;
-    bias[j] = (key < Lk && (kpm == nullptr || kpm[static_cast<int64_t>(b) * Lk + key] == 0)) ? 0.f : -INFINITY;
-  }
-}
-
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_raw);
-  const int q0 = blockIdx.x * kAB, h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = warp * 16 + (lane >> 1);           // this lane's query row inside the block
-  const int cbeg = (lane & 1) * 32;                   // and its 32 key columns
-  const int64_t qbase = static_cast<int64_t>(b) * a.Lq, kbase = static_cast<int64_t>(b) * a.Lk;
-
-  attn_load_block(sm.q, a.q, a.ldq, q0, a.Lq, qbase, h * 64);
-  attn_load_block(sm.dO, a.dO, a.lddo, q0, a.Lq, qbase, h * 64);
-  // delta_i = <do_i, o_i>: two lanes per row, 32 features each
-  float delta = 0.f;
-  if (q0 + row < a.Lq) {
-    const bf16* po = a.o + (qbase + q0 + row) * a.ldo + h * 64 + cbeg;
-    const bf16* pd = a.dO + (qbase + q0 + row) * a.lddo + h * 64 + cbeg;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(po + j));
-      const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pd + j));
-      delta += x.x * y.x + x.y * y.y;
-    }
-  }
-  delta += __shfl_xor_sync(0xffffffffu, delta, 1);
-
-  // ---- pass 1: lse_i -------------------------------------------------------------------------
-  float m = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < a.Lk; k0 += kAB) {
-    __syncthreads();
-    attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
-    attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
-    __syncthreads();
-    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
-    acc_zero(acc);
-    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);
-    acc_store(acc, &sm.s[warp * 16][0]);
-    __syncwarp();
-    float bm = -INFINITY;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) bm = fmaxf(bm, sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j]);
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-    const float mn = fmaxf(m, bm);
-    const float ref = mn == -INFINITY ? 0.f : mn;      // all keys so far masked: every term below is exp(-inf) = 0
-    float ps = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) ps += __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - ref);
-    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-    l = l * __expf(m - ref) + ps;
-    m = mn;
-    __syncwarp();
-  }
-  const float lse = m + __logf(l);
-  if ((lane & 1) == 0 && q0 + row < a.Lq) {
-    const int64_t idx = (static_cast<int64_t>(b) * a.H + h) * a.Lq + q0 + row;
-    a.lse[idx] = lse;
-    a.delta[idx] = delta;
-  }
-
-  // ---- pass 2: dq ----------------------------------------------------------------------------
-  wm::fragment<wm::accumulator, 16, 16, 16, float> dq[4];
-  acc_zero(dq);
-  for (int k0 = 0; k0 < a.Lk; k0 += kAB) {
-    __syncthreads();
-    attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
-    attn_load_block(sm.v, a.v, a.ldv, k0, a.Lk, kbase, h * 64);
-    attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
-    __syncthreads();
-    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
-    acc_zero(acc);
-    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);
-    acc_store(acc, &sm.s[warp * 16][0]);
-    acc_zero(acc);
-    mm_a_bt(acc, &sm.dO[warp * 16][0], sm.v);
-    acc_store(acc, &sm.dp[warp * 16][0]);
-    __syncwarp();
-#pragma unroll 8
-    for (int j = 0; j < 32; j += 2) {
-      const float p0 = __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - lse);
-      const float p1 = __expf(sm.s[row][cbeg + j + 1] * kAttScale + sm.bias[cbeg + j + 1] - lse);
-      const float d0 = p0 * (sm.dp[row][cbeg + j] - delta), d1 = p1 * (sm.dp[row][cbeg + j + 1] - delta);
-      *reinterpret_cast<uint32_t*>(&sm.ds[row][cbeg + j]) = pack_bf16x2(d0, d1);
-    }
-    __syncwarp();
-    mm_a_b(dq, &sm.ds[warp * 16][0], sm.k);
-  }
-  __syncwarp();
-  acc_store(dq, &sm.s[warp * 16][0]);
-  __syncwarp();
-  if (q0 + row < a.Lq) {
-    bf16* pq = a.dq + (qbase + q0 + row) * a.lddq + h * 64 + cbeg;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2)
-      *reinterpret_cast<uint32_t*>(pq + j) = pack_bf16x2(sm.s[row][cbeg + j] * kAttScale, sm.s[row][cbeg + j + 1] * kAttScale);
-  }
-}
-
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  AttnBwdSmem& sm = *reinterpret_cast<AttnBwdSmem*>(smem_raw);
-  const int k0 = blockIdx.x * kAB, h = blockIdx.y, b = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = warp * 16 + (lane >> 1);
-  const int cbeg = (lane & 1) * 32;
-  const int64_t qbase = static_cast<int64_t>(b) * a.Lq, kbase = static_cast<int64_t>(b) * a.Lk;
-
-  attn_load_block(sm.k, a.k, a.ldk, k0, a.Lk, kbase, h * 64);
-  attn_load_block(sm.v, a.v, a.ldv, k0, a.Lk, kbase, h * 64);
-  attn_fill_bias(sm.bias, a.kpm, b, a.Lk, k0);
-  wm::fragment<wm::accumulator, 16, 16, 16, float> dk[4], dv[4];
-  acc_zero(dk);
-  acc_zero(dv);
-  for (int q0 = 0; q0 < a.Lq; q0 += kAB) {
-    __syncthreads();
-    attn_load_block(sm.q, a.q, a.ldq, q0, a.Lq, qbase, h * 64);
-    attn_load_block(sm.dO, a.dO, a.lddo, q0, a.Lq, qbase, h * 64);
-    for (int j = threadIdx.x; j < kAB; j += blockDim.x) {
-      const bool ok = q0 + j < a.Lq;
-      const int64_t idx = (static_cast<int64_t>(b) * a.H + h) * a.Lq + q0 + j;
-      sm.lse[j] = ok ? a.lse[idx] : INFINITY;          // rows beyond Lq: p = exp(-inf) = 0
-      sm.delta[j] = ok ? a.delta[idx] : 0.f;
-    }
-    __syncthreads();
-    wm::fragment<wm::accumulator, 16, 16, 16, float> acc[4];
-    acc_zero(acc);
-    mm_a_bt(acc, &sm.q[warp * 16][0], sm.k);          // s[query, key]
-    acc_store(acc, &sm.s[warp * 16][0]);
-    acc_zero(acc);
-    mm_a_bt(acc, &sm.dO[warp * 16][0], sm.v);         // dp[query, key]
-    acc_store(acc, &sm.dp[warp * 16][0]);
-    __syncwarp();
-    const float lse = sm.lse[row], delta = sm.delta[row];
-#pragma unroll 8
-    for (int j = 0; j < 32; j += 2) {
-      const float p0 = __expf(sm.s[row][cbeg + j] * kAttScale + sm.bias[cbeg + j] - lse);
-      const float p1 = __expf(sm.s[row][cbeg + j + 1] * kAttScale + sm.bias[cbeg + j + 1] - lse);
-      const float d0 = p0 * (sm.dp[row][cbeg + j] - delta), d1 = p1 * (sm.dp[row][cbeg + j + 1] - delta);
-      *reinterpret_cast<uint32_t*>(&sm.p[row][cbeg + j]) = pack_bf16x2(p0, p1);
-      *reinterpret_cast<uint32_t*>(&sm.ds[row][cbeg + j]) = pack_bf16x2(d0, d1);
-    }
-    __syncthreads();
-    mm_at_b(dv, sm.p, warp * 16, sm.dO);              // dv[key, :] += p^T do
-    mm_at_b(dk, sm.ds, warp * 16, sm.q);              // dk[key, :] += ds^T q
-  }
-  __syncthreads();
-  acc_store(dv, &sm.s[warp * 16][0]);
-  acc_store(dk, &sm.dp[warp * 16][0]);
-  __syncwarp();
-  if (k0 + row < a.Lk) {
-    bf16* pv = a.dv + (kbase + k0 + row) * a.lddv + h * 64 + cbeg;
-    bf16* pk = a.dk + (kbase + k0 + row) * a.lddk + h * 64 + cbeg;
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      *reinterpret_cast<uint32_t*>(pv + j) = pack_bf16x2(sm.s[row][cbeg + j], sm.s[row][cbeg + j + 1]);
-      *reinterpret_cast<uint32_t*>(pk + j) = pack_bf16x2(sm.dp[row][cbeg + j] * kAttScale, sm.dp[row][cbeg + j + 1] * kAttScale);
-    }
-  }
-}
-
 static int elementwise_blocks(size_t n, int per_block) {
   size_t blocks = (n + per_block - 1) / per_block;
   const size_t cap = static_cast<size_t>(num_sms()) * 16;
@@ -884,21 +613,5 @@ extern "C" int tan_attention_bwd_bf16(const void* q, int64_t ldq, const void* k,
   a.dv = static_cast<bf16*>(dv); a.lddv = lddv;
   a.lse = lse; a.delta = delta;
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
-  // default: tcgen05 kernels (attention_bwd_tc.cu).  TAN_ATTN_BWD=pipe / mma / wmma select the legacy mma.sync /
-  // wmma versions (A/B aids; they recompute lse themselves and overwrite the buffer in their own layout)
-  static const char mode = [] { const char* e = getenv("TAN_ATTN_BWD"); return e == nullptr ? 't' : e[0]; }();
-  if (mode == 't') return attention_bwd_tc(a, static_cast<cudaStream_t>(stream));
-  static const bool use_wmma = mode == 'w';
-  static const bool use_pipe = mode == 'p';
-  if (use_pipe && attention_bwd_pipe_supported(a)) return attention_bwd_mma_pipe(a, static_cast<cudaStream_t>(stream));
-  if (!use_wmma) return attention_bwd_mma(a, static_cast<cudaStream_t>(stream));
-  const int smem = static_cast<int>(sizeof(AttnBwdSmem)) + 128;
-  TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  TAN_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  attn_bwd_dq_kernel<<<dim3((Lq + kAB - 1) / kAB, H, B), 128, smem, st>>>(a);
-  TAN_CUDA(cudaGetLastError());
-  attn_bwd_dkv_kernel<<<dim3((Lk + kAB - 1) / kAB, H, B), 128, smem, st>>>(a);
-  TAN_CUDA(cudaGetLastError());
-  return TAN_OK;
+  return attention_bwd_tc(a, static_cast<cudaStream_t>(stream));
 }

@@ -251,26 +251,48 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
     return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel, reduce_cols=False)
 
 
-def nce_losses_pair(logits_dual, logits_joint, nce: NceInputs, shard: bool):
-    """(loss_dual, loss_joint).  Sharded + fused path: the exchange of BOTH models is batched into one
-    all-gather (text features of the dual model stacked on the joint model's stages), one all-reduce (column
-    sums) and one tiny all-reduce (row sums / counts) -- the collectives are latency-bound at these sizes
-    (1-6 MB per rank), so their number, not their volume, is what a step pays for."""
-    dist = _dist() if shard else None
-    if dist is None or not (isinstance(logits_dual, LazyLogits) and isinstance(logits_joint, LazyLogits)):
-        return nce_loss_one_model(logits_dual, nce, shard), nce_loss_one_model(logits_joint, nce, shard)
-    vd, vj = logits_dual.vfeat, logits_joint.vfeat
-    td, tj = logits_dual.tfeat, logits_joint.tfeat                       # [B_loc*N, d], [Sj, B_loc*N, d]
+def pack_text_features(td: torch.Tensor, tj: torch.Tensor) -> torch.Tensor:
+    """[1 + Sj, B_loc*N, d]: the dual model's text features stacked on the joint model's stages.  The forward
+    allocates them as adjacent slices of one buffer (TemporalAligner._forward_impl), so this is normally a view."""
+    Sj, BN, d = tj.shape
+    if (td.is_contiguous() and tj.is_contiguous() and td.untyped_storage().data_ptr() == tj.untyped_storage().data_ptr()
+            and tj.storage_offset() == td.storage_offset() + BN * d):
+        return torch.as_strided(td, (1 + Sj, BN, d), (BN * d, d, 1))
+    return torch.cat((td[None], tj), dim=0).contiguous()
+
+
+_COALESCE = os.environ.get("TAN_GATHER_COALESCED", "1") != "0"
+
+
+def exchange_text_features(packed: torch.Tensor, dist) -> torch.Tensor:
+    """The one exchange step of the path: [1 + Sj, B_loc*N, d] per rank -> stage-major
+    [1 + Sj, W*B_loc*N, d] (global column c = rank * B_loc*N + local column), the layout the similarity kernel's 2-D
+    TMA map reads.  One coalesced NCCL launch of per-stage all-gathers writes that layout directly; the fallback is
+    one all-gather into a rank-major buffer + a permuting copy."""
+    W = dist.get_world_size()
+    S1, BN, d = packed.shape
+    full = torch.empty(S1, W * BN, d, dtype=packed.dtype, device=packed.device)
+    if _COALESCE and packed.is_cuda and hasattr(dist, "_coalescing_manager"):
+        try:
+            with dist._coalescing_manager(device=packed.device, async_ops=False):
+                for s in range(S1):
+                    dist.all_gather_into_tensor(full[s], packed[s])
+            return full
+        except Exception:                     # backend without coalescing support: fall through
+            pass
+    gathered = torch.empty(W * S1, BN, d, dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed)
+    return gathered.view(W, S1, BN, d).permute(1, 0, 2, 3).reshape(S1, W * BN, d).contiguous()
+
+
+def sim_pair_sums(vd, vj, full, nce: NceInputs):
+    """Fused similarity + exp-sum kernels of both models on the local rows x the columns of `full` [1 + Sj, C, d].
+    Returns (rs_d, cs_d, rs_j, cs_j, cols): `cols` is the flat buffer holding both column-sum tensors (one
+    all-reduce)."""
     B, Sd, T, d = vd.shape
     Sj = vj.shape[1]
     dev = vd.device
-    W = dist.get_world_size()
-    BN = td.shape[0]
-    packed = torch.cat((td[None], tj), dim=0).contiguous()               # [1 + Sj, B_loc*N, d]
-    gathered = torch.empty(W * (1 + Sj), BN, d, dtype=packed.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered, packed)
-    full = gathered.view(W, 1 + Sj, BN, d).permute(1, 0, 2, 3).reshape(1 + Sj, W * BN, d).contiguous()
-    C = W * BN
+    C = full.shape[1]
     cols = torch.empty(2 * (Sd + Sj) * C, dtype=torch.float32, device=dev)
     cs_d, cs_j = cols[:2 * Sd * C].view(2, Sd, C), cols[2 * Sd * C:].view(2, Sj, C)
     rs_d = torch.empty(2, B * Sd * T, dtype=torch.float32, device=dev)
@@ -280,8 +302,24 @@ def nce_losses_pair(logits_dual, logits_joint, nce: NceInputs, shard: bool):
     ws = torch.empty(max(ops.sim_workspace_bytes(g_d), ops.sim_workspace_bytes(g_j)), dtype=torch.uint8, device=dev)
     ops.sim_nce_fwd(vd, full[0], 0, g_d, nce.posbits, nce.col_valid, None, rs_d, cs_d, ws, row_kill=nce.row_kill)
     ops.sim_nce_fwd(vj, full[1:], C * d, g_j, nce.posbits, nce.col_valid, None, rs_j, cs_j, ws, row_kill=nce.row_kill)
+    return rs_d, cs_d, rs_j, cs_j, cols
+
+
+def nce_losses_pair(logits_dual, logits_joint, nce: NceInputs, shard: bool):
+    """(loss_dual, loss_joint).  Sharded + fused path: the exchange of BOTH models is batched into one gather of the
+    text features (dual model's stacked on the joint model's stages), one all-reduce (column sums) and one tiny
+    all-reduce (row sums / counts) -- the collectives are latency-bound at these sizes (1-6 MB per rank), so their
+    number, not their volume, is what a step pays for."""
+    dist = _dist() if shard else None
+    if dist is None or not (isinstance(logits_dual, LazyLogits) and isinstance(logits_joint, LazyLogits)):
+        return nce_loss_one_model(logits_dual, nce, shard), nce_loss_one_model(logits_joint, nce, shard)
+    vd, vj = logits_dual.vfeat, logits_joint.vfeat
+    Sd, T, Sj = vd.shape[1], vd.shape[2], vj.shape[1]
+    full = exchange_text_features(pack_text_features(logits_dual.tfeat, logits_joint.tfeat), dist)
+    C = full.shape[1]
+    rs_d, cs_d, rs_j, cs_j, cols = sim_pair_sums(vd, vj, full, nce)
     dist.all_reduce(cols)
-    out8 = torch.zeros(8, dtype=torch.float64, device=dev)
+    out8 = torch.zeros(8, dtype=torch.float64, device=vd.device)
     ops.nce_reduce(rs_d, cs_d, out8[0:4], Sd, T, C, nce.row_sel, nce.col_sel)
     ops.nce_reduce(rs_j, cs_j, out8[4:8], Sj, T, C, nce.row_sel, nce.col_sel)
     rows = torch.cat((out8[0:2], out8[4:6]))

@@ -1,14 +1,16 @@
-"""Step runner for the TAN hot path: one step = TemporalAligner.forward + get_loss (`--model init`)
-over one batch of clips.  Used by bench.py and the multi-GPU tests.
+"""Step runner for the TAN hot path: one step = TemporalAligner.forward + get_loss over one batch of clips.
+Used by bench.py and the multi-GPU check scripts.
 
-  * `step_api(batch_host)`   the public API exactly as train/main.py:81-105 calls it, starting from
-                             HOST tensors / python lists: H2D copies, forward, get_loss, `.item()`.
-  * `step_resident()`        same kernels on inputs already resident in HBM, no host sync; with
-                             `use_graph=True` the whole step (about 100 kernel launches) is replayed
-                             from one CUDA graph, which removes the launch-bound gaps at small shapes.
+  * `run_api_steps(n)`       the public API exactly as train/main.py:81-105 calls it, starting from pinned HOST
+                             tensors / python lists: H2D copies, forward, get_loss, `.item()`.
+  * `step_resident()`        same kernels on inputs already resident in HBM, no host sync; with `use_graph=True` the
+                             whole step (about 100 kernel launches) is replayed from one CUDA graph.
+  * `step_train()`           forward with tape + get_loss + loss.backward() (no optimizer).
 
-Multi-GPU (one process per GPU): each rank holds B_loc clips; the contrastive matrix spans the
-global batch (loss.py all-gathers text features / targets and all-reduces column sums).
+Multi-GPU (one process per GPU): ONE global batch is generated from the seed and every rank takes its slice
+[rank * B_loc, (rank + 1) * B_loc), so the loss of the global batch is the same number at every world size (a free
+cross-N parity check); the contrastive matrix spans the global batch (loss.py all-gathers text features / targets
+and all-reduces column sums).
 """
 from __future__ import annotations
 
@@ -23,37 +25,57 @@ from . import ops, synth
 from .tan_model import TemporalAligner
 
 
-def default_loss_args():
-    return types.SimpleNamespace(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep",
-                                 loss_threshold=0.0, use_alignability_head=0, optim_policy="default")
+def default_loss_args(**kw):
+    d = dict(model="init", sim="cos", learn_agreement=0, temporal_agreement_type="keep", loss_threshold=0.0,
+             use_alignability_head=0, optim_policy="default")
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def slice_batch(batch: dict, lo: int, hi: int) -> dict:
+    """Clips [lo, hi) of a synth.make_batch dict."""
+    out = {}
+    for k, v in batch.items():
+        out[k] = v[lo:hi]
+    return out
 
 
 class TanStepRunner:
     def __init__(self, num_encoder_layers=6, num_decoder_layers=6, B_loc=32, T=256, N=None, width=512,
-                 video_dim=1024, seed=888, device="cuda", rank=0, world_size=1, use_graph=True):
+                 video_dim=1024, seed=888, device="cuda", rank=0, world_size=1, use_graph=True, loss_flags=None):
         self.E, self.D, self.B, self.T = num_encoder_layers, num_decoder_layers, B_loc, T
         self.N = N if N is not None else max(T // 8, 1)
         self.width, self.video_dim = width, video_dim
         self.device = torch.device(device)
         self.rank, self.world = rank, world_size
         self.shard = world_size > 1
-        # one GPU: the whole step (forward + loss) is one CUDA graph; several GPUs: the forward (no
-        # collectives) replays from the model's own graph cache and the loss (NCCL all-gather / all-reduce
-        # + a dozen launches) is enqueued eagerly behind it
-        # (capturing the NCCL collectives as well was measured at -3 % step time on 2 GPUs and hung at
-        # process-group teardown, so it is not offered)
-        self.use_graph = use_graph and world_size == 1
+        self.flags = dict(loss_flags or {})
+        self.args = default_loss_args(**self.flags)
+        # loss recipes with flags (config 5) run through get_loss itself: python glue on [B*N] vectors, pinned
+        # staging buffers -> eager launches.  The plain recipe is graph-captured: one GPU: the whole step is one CUDA
+        # graph; several GPUs: the forward (no collectives) replays from the model's own graph cache and the loss
+        # (NCCL all-gather / all-reduce + a dozen launches) is enqueued eagerly behind it, or -- TAN_GRAPH_NCCL=1 --
+        # captured together with its collectives
+        self.graph_nccl = os.environ.get("TAN_GRAPH_NCCL", "0") == "1"
+        self.use_graph = use_graph and not self.flags and (world_size == 1 or self.graph_nccl)
         self.use_model_graph = use_graph
-        self.args = default_loss_args()
-        sd = synth.make_state_dict(self.E, self.D, width=width, d_in=video_dim, seed=seed, perturb=False)
-        self.model = TemporalAligner(self.E, self.D, random_pos_start=0, width=width, video_dim=video_dim)
+        head = int(self.flags.get("use_alignability_head", 0))
+        sd = synth.make_state_dict(self.E, self.D, width=width, d_in=video_dim, seed=seed, perturb=False,
+                                   use_alignability_head=bool(head))
+        self.model = TemporalAligner(self.E, self.D, random_pos_start=0, width=width, video_dim=video_dim,
+                                     use_alignability_head=head)
         self.model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         self.model = self.model.to(self.device)
         if os.environ.get("TAN_TWO_STREAMS") is not None:            # A/B aid
             self.model.two_streams = os.environ["TAN_TWO_STREAMS"] != "0"
         if self.use_model_graph:
             self.model.enable_cuda_graphs(True)
-        self.batch = synth.make_batch(B_loc, T, self.N, d_in=video_dim, seed=seed, tag=f"rank{rank}")
+        # ONE global batch; this rank's slice
+        B_glob = B_loc * world_size
+        full = synth.make_batch(B_glob, T, self.N, d_in=video_dim, seed=seed, tag="global")
+        self.batch = slice_batch(full, rank * B_loc, (rank + 1) * B_loc)
+        self.global_n_b = [len(s) for s in full["start"]]
+        del full
         # pinned host copies (the e2e path starts here) and device-resident copies
         self.h_video = torch.from_numpy(self.batch["video"]).pin_memory()
         self.h_text = torch.from_numpy(self.batch["text"]).pin_memory()
@@ -73,16 +95,10 @@ class TanStepRunner:
         self.launches_per_step = None
 
     # -- the public-API step, from host memory ------------------------------------------------------
-    def step_api(self) -> float:
-        dev = self.device
-        video = self.h_video.to(dev, non_blocking=True)
-        text = self.h_text.to(dev, non_blocking=True)
-        vpm = self.h_vpm.to(dev, non_blocking=True)
-        tpm = self.h_tpm.to(dev, non_blocking=True)
+    def _api_step(self, video, text, vpm, tpm):
         out = self.model(video, text, video_padding_mask=vpm, lang_padding_mask=tpm, text_timestamp=None,
                          abs_text_pos=None)
-        ld = loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
-        return ld["loss"].item()                              # D2H read of the step's result
+        return loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
 
     def run_api_steps(self, n: int) -> float:
         """n public-API steps with the NEXT step's host->device copies issued on a copy stream while the current
@@ -116,15 +132,15 @@ class TanStepRunner:
             slot = i & 1
             main.wait_event(ready[slot])
             video, text, vpm, tpm = self._stage[slot]
-            out = self.model(video, text, video_padding_mask=vpm, lang_padding_mask=tpm, text_timestamp=None,
-                             abs_text_pos=None)
-            ld = loss_mod.get_loss(self.input_data, video, text, vpm, tpm, out, self.args, None, shard_batch=self.shard)
+            ld = self._api_step(video, text, vpm, tpm)
             consumed[slot].record(main)
             loss = ld["loss"].item()                                  # D2H read of the step's result
         return loss
 
     # -- device-resident step -----------------------------------------------------------------------
     def _step_kernels(self) -> torch.Tensor:
+        if self.flags:
+            return self._api_step(self.d_video, self.d_text, self.d_vpm, self.d_tpm)["loss"]
         out = self.model(self.d_video, self.d_text, video_padding_mask=self.d_vpm, lang_padding_mask=self.d_tpm)
         l_dual, l_joint = loss_mod.nce_losses_pair(out["logits_dual"], out["logits_joint"], self.nce, self.shard)
         return (l_dual + l_joint) / 2
@@ -150,39 +166,19 @@ class TanStepRunner:
             torch.cuda.synchronize()
         return float(loss)
 
-    def class_graph(self, name: str):
-        """(graph, work, launches) holding ONLY the launches of kernel class `name` of one resident step
-        (ops.only_class).  bench.py replays it to get that kernel's average launch duration with CUDA
-        events alone -- per-launch event pairs on eagerly launched kernels also time the host's launch
-        preparation whenever the GPU runs dry."""
-        shard, self.shard = self.shard, False        # no collectives inside these measurement graphs
-        graphs_on, self.model._graphs_on = self.model._graphs_on, False
-        nce = self.nce
-        if shard:                                    # local columns only: the same kernels at the local geometry
-            lo = nce.b_off * nce.N
-            self.nce = loss_mod.NceInputs(nce.posbits, nce.col_valid[lo:lo + self.B * nce.N].contiguous(), nce.N, nce.T,
-                                          0, self.B)
-        try:
-            with ops.only_class(name) as acc:
-                self._step_kernels()                 # eager dry run: allocations
-                torch.cuda.synchronize()
-                acc[0], acc[1] = 0.0, 0
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_kernels()
-        finally:
-            self.shard = shard
-            self.nce = nce
-            self.model._graphs_on = graphs_on
-        g.replay()
-        torch.cuda.synchronize()
-        return g, acc[0], acc[1]
-
     def step_resident(self) -> torch.Tensor:
         if self._graph is not None:
             self._graph.replay()
             return self._graph_loss
         return self._step_kernels()
+
+    def close(self) -> None:
+        """Drop captured graphs (before the process group is destroyed: a graph holding NCCL kernels must not
+        outlive its communicator)."""
+        self._graph = None
+        self._graph_loss = None
+        self.model.enable_cuda_graphs(False)
+        torch.cuda.synchronize()
 
     # -- training step: forward with tape + get_loss + backward (no optimizer) -------------------------
     def step_train(self) -> torch.Tensor:

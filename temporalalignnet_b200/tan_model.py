@@ -284,7 +284,7 @@ class TemporalAligner(nn.Module):
         return raw, nrm
 
     def _run_joint_stack(self, pre_v, pre_t, B, T, N, kpm_v, kpm_t, pos_ln_v, pos_ln_t, want_raw_v, want_raw_t,
-                         want_nrm):
+                         want_nrm, nrm_t_out=None):
         """Joint stack over [video ; text] tokens (model/tan_model.py:182-209)."""
         d, D, dev = self.width, self.num_decoder_layers, pre_v.device
         L = T + N
@@ -302,7 +302,8 @@ class TemporalAligner(nn.Module):
         raw_v = torch.empty(B, D, T, d, dtype=torch.float32, device=dev) if want_raw_v else None
         raw_t = torch.empty(D, B, N, d, dtype=torch.float32, device=dev) if want_raw_t else None
         nrm_v = torch.empty(B, D, T, d, dtype=torch.bfloat16, device=dev) if want_nrm else None
-        nrm_t = torch.empty(D, B * N, d, dtype=torch.bfloat16, device=dev) if want_nrm else None
+        nrm_t = (nrm_t_out if nrm_t_out is not None else
+                 torch.empty(D, B * N, d, dtype=torch.bfloat16, device=dev)) if want_nrm else None
         sink = StageSink(D, l_split=T, strideA=D * T, strideB=N, rawA=raw_v, rawB=raw_t, nrmA_bf16=nrm_v,
                          nrmB_bf16=nrm_t, offA=T, offB=B * N)
         enc = self.joint_temporal_encoder
@@ -310,11 +311,12 @@ class TemporalAligner(nn.Module):
                           post_ln=self.ln_joint_post_enc)
         return raw_v, raw_t, nrm_v, nrm_t
 
-    def _text_features(self, pre_t, B, N, want_raw, want_nrm_bf16, want_nrm_f32):
+    def _text_features(self, pre_t, B, N, want_raw, want_nrm_bf16, want_nrm_f32, nrm_out=None):
         """ln_text_init(text_pre_proj(t)) (model/tan_model.py:231-234) + its L2-normalised copies."""
         d, dev = self.width, pre_t.device
         raw = torch.empty(B, N, d, dtype=torch.float32, device=dev) if want_raw else None
-        nb = torch.empty(B * N, d, dtype=torch.bfloat16, device=dev) if want_nrm_bf16 else None
+        nb = (nrm_out if nrm_out is not None else
+              torch.empty(B * N, d, dtype=torch.bfloat16, device=dev)) if want_nrm_bf16 else None
         nf = torch.empty(B, N, d, dtype=torch.float32, device=dev) if want_nrm_f32 else None
         ops.layernorm(pre_t, B * N, d, gamma=_f32(self.ln_text_init.weight), beta=_f32(self.ln_text_init.bias),
                       L_in=N, l_split=N, strideA=N, rawA=raw, nrmA_bf16=nb, nrmA_f32=nf)
@@ -433,15 +435,20 @@ class TemporalAligner(nn.Module):
         # (one wave of tiles, prologue, drain); the other stack's kernels fill those gaps.
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.two_streams else main
+        # the L2-normalised text features of the dual model and of every joint stage live in ONE buffer
+        # [1 + D, B*N, d]: the multi-GPU exchange gathers it without a packing copy (loss.pack_text_features)
+        tpack = torch.empty(1 + self.num_decoder_layers, B * N, self.width, dtype=torch.bfloat16, device=dev)
         if side is not main:
             side.wait_stream(main)
+            tpack.record_stream(side)
         with torch.cuda.stream(side):
             _, jt_raw, vfeat_joint, tfeat_joint = self._run_joint_stack(
                 pre_v, pre_t, B, T, N, kpm_v, kpm_t, pos_ln_j, pos_ln_t, want_raw_v=False, want_raw_t=head,
-                want_nrm=True)
+                want_nrm=True, nrm_t_out=tpack[1:])
         _, vfeat_dual = self._run_video_stack(pre_v, B, T, kpm_v, pos_ln_v, want_raw=False, want_nrm=True)
         text_raw, tfeat_dual, tfeat_dual_f32 = self._text_features(
-            pre_t, B, N, want_raw=head, want_nrm_bf16=True, want_nrm_f32=bool(self.return_dual_feature))
+            pre_t, B, N, want_raw=head, want_nrm_bf16=True, want_nrm_f32=bool(self.return_dual_feature),
+            nrm_out=tpack[0])
         if side is not main:
             main.wait_stream(side)
             for t_ in (jt_raw, vfeat_joint, tfeat_joint):

@@ -34,9 +34,6 @@ AUTOGRAD_DEFAULT = os.environ.get("TAN_AUTOGRAD", "0") != "0"
 SIM_BWD_ROWS = int(os.environ.get("TAN_SIM_BWD_ROWS", "65536"))
 SIM_BWD_G_BYTES = 2 << 30
 SIM_GRAD_FUSED = os.environ.get("TAN_SIM_GRAD_FUSED", "1") != "0"     # G in the epilogue of the recomputation GEMM
-SIM_GRAD_GT = os.environ.get("TAN_SIM_GRAD_GT", "0") == "1"           # experimental: G^T from the same epilogue
-# weight gradients / the text-side similarity gradient on MN-major operands (tan_gemm_tn_bf16): no transposes
-TN_GEMM = os.environ.get("TAN_TN_GEMM", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -259,62 +256,13 @@ class _Grads:
         return self.g.get(id(p))
 
 
-WGRAD_SPLIT = int(os.environ.get("TAN_WGRAD_SPLIT", "6"))      # concurrent K chunks of one weight-gradient GEMM
-_side_streams = {}
-
-
-def _streams(dev, n: int):
-    pool = _side_streams.setdefault(str(dev), [])
-    while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=dev))
-    return pool[:n]
-
-
-FUSE_BIAS_SUM = os.environ.get("TAN_FUSE_BIAS_SUM", "0") == "1"     # experimental: bias sums inside the dY transpose
-
-
 def _wgrad(dy_bf16: torch.Tensor, x_bf16: torch.Tensor, gw: torch.Tensor, gb: Optional[torch.Tensor] = None) -> None:
-    """gw [N, K] += dy^T @ x   (dy [M, N], x [M, K] bf16): the pair GEMM on the two transposes with fp32
-    accumulation.  A weight gradient has few output tiles (4 .. 16 of 256 x 256) and a long contraction (all tokens),
-    so one launch would occupy 4 .. 16 of the 74 CTA pairs: the contraction is split into chunks that run as
-    concurrent launches on side streams (each launch only takes as many CTA pairs as it has tiles) into partial
-    buffers, summed in a fixed order by tan_colsum (deterministic).  gb [N]: the bias gradient (column sums of dy),
-    accumulated by tan_colsum or, experimentally, by the transpose of dy itself."""
-    if TN_GEMM and dy_bf16.shape[1] % 8 == 0 and x_bf16.shape[1] % 32 == 0:
-        if gb is not None:
-            ops.colsum(dy_bf16, gb)
-        ops.gemm_tn(dy_bf16, x_bf16, gw, accumulate=True)
-        return
-    if gb is not None and FUSE_BIAS_SUM:
-        dyT = ops.transpose_colsum_bf16(dy_bf16, gb)
-    else:
-        if gb is not None:
-            ops.colsum(dy_bf16, gb)
-        dyT = ops.transpose_bf16(dy_bf16)      # [N, pad64(M)]
-    xT = ops.transpose_bf16(x_bf16)            # [K, pad64(M)]
-    N, Mp = dyT.shape
-    K = xT.shape[0]
-    tiles = ((N + 255) // 256) * ((K + 255) // 256)
-    split = min(WGRAD_SPLIT, max(1, 74 // tiles), Mp // 2048)
-    if split <= 1:
-        ops.linear(dyT, xT, residual=gw, out_f32=gw, tag="wgrad")
-        return
-    dev = dyT.device
-    Kc = ops.pad64((Mp + split - 1) // split)
-    split = (Mp + Kc - 1) // Kc
-    partial = torch.empty(split, N, K, dtype=torch.float32, device=dev)
-    main = torch.cuda.current_stream(dev)
-    start = torch.cuda.Event()
-    start.record(main)
-    for j, st in enumerate(_streams(dev, split)):
-        st.wait_event(start)
-        with torch.cuda.stream(st):
-            k0, k1 = j * Kc, min((j + 1) * Kc, Mp)
-            ops.linear(dyT[:, k0:k1], xT[:, k0:k1], out_f32=partial[j], tag="wgrad")
-            done = torch.cuda.Event()
-            done.record(st)
-        main.wait_event(done)
-    ops.colsum(partial.view(split, N * K), gw.view(-1), accumulate=True)
+    """gw [N, K] += dy^T @ x   (dy [M, N], x [M, K] bf16): tan_gemm_tn_bf16 consumes both operands as they lie in HBM
+    (MN-major UMMA operands) and splits the long contraction over the CTA pairs inside the one launch (fixed-order
+    partial sums: deterministic).  gb [N]: the bias gradient (column sums of dy)."""
+    if gb is not None:
+        ops.colsum(dy_bf16, gb)
+    ops.gemm_tn(dy_bf16, x_bf16, gw, accumulate=True)
 
 
 def _dgrad(dy_bf16: torch.Tensor, wT: torch.Tensor, out_f32=None, out_bf16=None, residual=None) -> None:
@@ -435,41 +383,30 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
     R = B * T
     Rc = min(R, SIM_BWD_ROWS, max(256, (SIM_BWD_G_BYTES // (2 * Cp)) // 256 * 256))
     g = ops.sim_geom(B, 1, T, C, nce.N, d, nce.b_off)
-    fused = SIM_GRAD_FUSED and nce.N <= 64
+    fused = SIM_GRAD_FUSED and nce.N <= 64 and d % 64 == 0
     z = None if fused else torch.empty(Rc, Cp, dtype=torch.float32, device=dev)
     G = torch.empty(Rc, Cp, dtype=torch.bfloat16, device=dev)
-    GT = torch.empty(Cp if fused else C, ops.pad64(Rc), dtype=torch.bfloat16, device=dev)
+    GT = None if fused else torch.empty(C, ops.pad64(Rc), dtype=torch.bfloat16, device=dev)
     d_v = torch.empty(S, R, d, dtype=torch.float32, device=dev)
     d_t = torch.zeros(S_t, Cp, d, dtype=torch.float32, device=dev)
     for s in range(S):
         si = 0 if lg.shared_text else s
         ts = tpad[si]
-        tT = ops.transpose_bf16(ts)                                           # [d, Cp]
+        tT = ops.transpose_bf16(ts)                                           # [d, Cp] (small: the text side)
         for r0 in range(0, R, Rc):
             rc = min(Rc, R - r0)
             a = vsm[s, r0:r0 + rc]
-            if fused and SIM_GRAD_GT:     # experimental: the epilogue writes G^T as well (no transpose pass)
-                ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
-                                  G[:rc], GT=GT[:, :ops.pad64(rc)])
-            elif fused and TN_GEMM and d % 32 == 0:
-                # cosines recomputed and turned into G inside one GEMM; dB = G^T @ video straight from G and the
-                # video rows as they lie (MN-major operands): no transpose of either
+            if fused:
+                # cosines recomputed and turned into G inside ONE GEMM (epilogue); the fp32 cosines never reach HBM
                 ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
                                   G[:rc])
-                ops.linear(G[:rc], tT, out_f32=d_v[s, r0:r0 + rc], tag="sim_bwd")                # dA = G @ text
-                ops.gemm_tn(G[:rc], a, d_t[si], accumulate=True, tag="sim_bwd")                  # dB += G^T @ video
-                continue
-            elif fused:    # cosines recomputed and turned into G inside one GEMM; G^T by the transpose kernel
-                ops.sim_grad_gemm(a, ts, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s], cbp[s],
-                                  G[:rc])
-                ops.transpose_bf16(G[:rc], GT[:, :ops.pad64(rc)])
             else:
                 ops.linear(a, ts, out_f32=z[:rc], tag="sim_bwd")                             # cosines of the chunk
                 ops.sim_grad_tiles(z, rc, r0, g, nce.posbits, nce.col_valid, nce.row_kill, ra[s], rap[s], cb[s],
                                    cbp[s], G, GT)
             ops.linear(G[:rc], tT, out_f32=d_v[s, r0:r0 + rc], tag="sim_bwd")                # dA = G @ text
-            aT = ops.transpose_bf16(a)                                        # [d, pad64(rc)]
-            ops.linear(GT[:C, :ops.pad64(rc)], aT, residual=d_t[si, :C], out_f32=d_t[si, :C], tag="sim_bwd")   # dB += G^T @ video
+            # dB += G^T @ video straight from G and the video rows as they lie (MN-major operands): no transposes
+            ops.gemm_tn(G[:rc], a, d_t[si], accumulate=True, tag="sim_bwd")
     return d_v, d_t
 
 

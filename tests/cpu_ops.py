@@ -138,11 +138,6 @@ def transpose_bf16(x, out=None):
     return out
 
 
-def transpose_colsum_bf16(x, colsum_out, accumulate=True):
-    colsum(x, colsum_out, accumulate)
-    return transpose_bf16(x)
-
-
 def ema_update(target_params, online_params, m):
     """Stand-in of optim.ema_update (tan_ema_update): in place on the Parameters, so version counters advance."""
     with torch.no_grad():
@@ -301,7 +296,7 @@ def agree_scan(own, posbits, vpm_u8, tpm_u8, B, T, N, fill_max):
     return win, torch.zeros(B, N), z.max(dim=1).values
 
 
-NAMES = ["gemm_tn", "own_clip_sim", "agree_scan", "transpose_colsum_bf16", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
+NAMES = ["gemm_tn", "own_clip_sim", "agree_scan", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
          "transpose_bf16", "colsum", "layernorm_bwd", "l2norm_bwd", "batch_sum", "sim_grad_gemm", "sim_grad_tiles",
          "pos_from_time", "sim_workspace_bytes", "sim_nce_fwd", "nce_reduce"]
 

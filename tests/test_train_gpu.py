@@ -136,108 +136,22 @@ def test_sgd_step_reduces_loss():
     assert losses[-1] < losses[0], losses
 
 
-def test_wgrad_split_over_streams():
-    """Weight gradient with the contraction split into concurrent chunks (train._wgrad) == dy^T @ x."""
+def test_wgrad_split_contraction_deterministic():
+    """Weight gradient with the contraction split over the CTA pairs inside one launch (train._wgrad ->
+    tan_gemm_tn_bf16) == dy^T @ x, bias gradient == column sums, bit-identical on a re-run."""
     from temporalalignnet_b200 import train
     g = torch.Generator().manual_seed(3)
     M, N, K = 12288 + 100, 512, 1024
     dy = (torch.randn(M, N, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
     x = torch.randn(M, K, generator=g).to(DEV).to(torch.bfloat16)
     gw = torch.ones(N, K, dtype=torch.float32, device=DEV)
-    train._wgrad(dy, x, gw)
+    gb = torch.zeros(N, dtype=torch.float32, device=DEV)
+    train._wgrad(dy, x, gw, gb)
     torch.cuda.synchronize()
     ref = 1.0 + dy.float().t() @ x.float()
     assert ((gw - ref).norm() / ref.norm()).item() < 1e-4
+    assert (gb - dy.float().sum(0)).abs().max().item() < 1e-2
     gw2 = torch.ones(N, K, dtype=torch.float32, device=DEV)
     train._wgrad(dy, x, gw2)
     torch.cuda.synchronize()
     assert torch.equal(gw, gw2)                               # fixed-order partial sums: deterministic
-
-
-def test_cotrain_twin_step_runs():
-    """Stage-2 recipe (train/main.py:88-123): online forward with autograd, EMA forward, get_loss(model='cotrain',
-    learn_agreement=1), backward, optimizer step, momentum update."""
-    from temporalalignnet_b200 import TwinTemporalAligner, get_loss
-    cfg, sd, batch, _ = case_inputs("g1_e1d1_T32_B4")
-    m = TwinTemporalAligner(m=0.99, num_encoder_layers=1, num_decoder_layers=1, random_pos_start=0).to(DEV)
-    m.online.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
-    m._copy_param()
-    m.train()
-    m.enable_autograd(True)
-    opt = torch.optim.SGD([p for p in m.parameters() if p.requires_grad], lr=0.01)
-    video, text = torch.from_numpy(batch["video"]).to(DEV), torch.from_numpy(batch["text"]).to(DEV)
-    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
-    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
-    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
-    ema = m.forward_from_ema(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
-    out.update({"ema-" + k: v for k, v in ema.items()})
-    input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
-    res = get_loss(input_data, video, text, vpm.float(), tpm.float(), out, _args(model="cotrain", learn_agreement=1),
-                   None)
-    assert res["loss"].requires_grad and "confidence-ratio" in res
-    w0 = m.target.video_pre_proj.weight.detach().clone()
-    res["loss"].backward()
-    got = [p.grad for p in m.online.parameters() if p.grad is not None]
-    assert len(got) >= 37 and all(torch.isfinite(g).all() for g in got)
-    assert all(p.grad is None for p in m.target.parameters())
-    opt.step()
-    m._momentum_update()
-    assert not torch.equal(w0, m.target.video_pre_proj.weight)
-
-
-def test_backward_with_alignability_head_vs_oracle_autograd():
-    """BASELINE config 5's loss recipe at toy size: thresholded NCE + BCE of the alignability head on joint stage 2
-    (train/loss.py:306-357): gradients reach binary_head and, through it, the joint stack."""
-    from temporalalignnet_b200 import get_loss
-    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
-    args = _args(loss_threshold=0.5, use_alignability_head=1)
-    ref_loss, ref_grads = _oracle_grads(cfg, sd, batch, args)
-    m = _build(cfg, sd, head=1)
-    m.enable_autograd(True)
-    video, text = torch.from_numpy(batch["video"]).to(DEV), torch.from_numpy(batch["text"]).to(DEV)
-    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
-    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
-    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
-    input_data = {"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}
-    res = get_loss(input_data, video, text, vpm.float(), tpm.float(), out, args, None)
-    assert abs(res["loss"].item() - ref_loss) < 2e-3 * abs(ref_loss), (res["loss"].item(), ref_loss)
-    res["loss"].backward()
-    torch.cuda.synchronize()
-    assert m.binary_head.weight.grad is not None and m.binary_head.bias.grad is not None
-    _compare(m, ref_grads, loose=True)
-
-
-def test_gradients_reach_the_text_and_video_inputs():
-    """`lang_embed` / `video_embed` that require grad (the reference trains the text backbone through lang_embed,
-    train/main.py:58-60) receive their gradient from the step's autograd node; checked against oracle autograd."""
-    from oracle import tan_oracle as O
-    from temporalalignnet_b200 import get_loss
-    cfg, sd, batch, _ = case_inputs("g2_e2d3_T24_B3")
-    cfg = dict(cfg, head=0)
-    sd = {k: v for k, v in sd.items() if not k.startswith("binary_head")}
-    m = _build(cfg, sd)
-    m.enable_autograd(True)
-    scale = torch.nn.Parameter(torch.ones(512, device=DEV))
-    text0 = torch.from_numpy(batch["text"]).to(DEV)
-    video = torch.from_numpy(batch["video"]).to(DEV).requires_grad_(True)
-    vpm = torch.from_numpy(batch["video_padding_mask"]).to(DEV)
-    tpm = torch.from_numpy(batch["text_padding_mask"]).to(DEV)
-    text = text0 * scale
-    out = m(video, text, video_padding_mask=vpm, lang_padding_mask=tpm)
-    res = get_loss({"start": batch["start"], "end": batch["end"], "text": batch["text_str"]}, video, text,
-                   vpm.float(), tpm.float(), out, _args(), None)
-    res["loss"].backward()
-    torch.cuda.synchronize()
-    sd_t = {k: torch.from_numpy(v) for k, v in sd.items()}
-    orc = O.TanOracle(sd_t, cfg["E"], cfg["D"], use_text_pos_enc=cfg["use_text_pos_enc"])
-    scale_r = torch.ones(512, requires_grad=True)
-    video_r = torch.from_numpy(batch["video"]).clone().requires_grad_(True)
-    ro = orc.forward(video_r, torch.from_numpy(batch["text"]) * scale_r, batch["video_padding_mask"],
-                     batch["text_padding_mask"])
-    O.get_loss_init(ro["logits_dual"], ro["logits_joint"], batch["start"], batch["end"],
-                    batch["text_padding_mask"])["loss"].backward()
-    for got, ref in ((scale.grad, scale_r.grad), (video.grad, video_r.grad)):
-        g, r = got.detach().float().cpu().double().reshape(-1), ref.double().reshape(-1)
-        cos = float((g @ r) / (g.norm() * r.norm()))
-        rel = float((g - r).norm() / r.norm())
-        assert cos > 0.999 and rel < 3e-2, (cos, rel)
