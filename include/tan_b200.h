@@ -44,6 +44,7 @@ extern "C" {
 /* Epilogue activation for tan_linear_bf16. */
 #define TAN_ACT_NONE 0
 #define TAN_ACT_QUICKGELU 1 /* x * sigmoid(1.702 x), model/tfm_model.py:11-13 */
+#define TAN_ACT_RELU 2      /* max(x, 0), model/word2vec_model.py:86 */
 
 /* ---- library ------------------------------------------------------------------------------- */
 

@@ -292,6 +292,65 @@ def run_align():
     print("g_align", {k: v.shape for k, v in out.items()})
 
 
+def make_word2vec_case(V=500, S=7, seed=888):
+    """Seeded weights / tokens of a small Word2VecModel (vocabulary V instead of 66250; same layer sizes): sentence 2
+    consists of stop words only (all ids 0 -> attention mask all zero, model/word2vec_model.py:93), sentence 3 repeats
+    a word (tie of the max-pool)."""
+    sd = {"word_embd.weight": synth._normal("w2v.word_embd", seed, (V, 300), 0.3),
+          "fc1.weight": synth._normal("w2v.fc1.weight", seed, (2048, 300), 0.05),
+          "fc1.bias": synth._normal("w2v.fc1.bias", seed, (2048,), 0.1),
+          "fc2.weight": synth._normal("w2v.fc2.weight", seed, (512, 2048), 0.03),
+          "fc2.bias": synth._normal("w2v.fc2.bias", seed, (512,), 0.1)}
+    r = synth._rng("w2v.tokens", seed)
+    ids = np.zeros((S, 32), np.int64)
+    for s_ in range(S):
+        n = int(r.integers(1, 33))
+        ids[s_, :n] = r.integers(1, V, size=n)
+    ids[2, :] = 0
+    ids[3, :4] = ids[3, 0]
+    return sd, ids
+
+
+def run_word2vec():
+    """Word2VecModel.forward of the reference (model/word2vec_model.py:83-101) on synthetic weights: the class needs
+    the S3D checkpoint to CONSTRUCT (:79), so an instance is made without __init__ and given its three sub-modules."""
+    import importlib.util
+    # the real module file (load_reference() registers a STUB under the name `word2vec_model`); its only missing
+    # import is the S3D class of the MIL-NCE checkpoint code (model/word2vec_model.py:8), unused by forward()
+    sys.modules.setdefault("s3d_milnce", types.ModuleType("s3d_milnce"))
+    s3dg = types.ModuleType("s3d_milnce.s3dg")
+    s3dg.S3D = object
+    sys.modules.setdefault("s3d_milnce.s3dg", s3dg)
+    from oracle.ref_loader import REF_ROOT
+    spec = importlib.util.spec_from_file_location("ref_word2vec_model", os.path.join(REF_ROOT, "model", "word2vec_model.py"))
+    w2v = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(w2v)
+    sd, ids = make_word2vec_case()
+    m = w2v.Word2VecModel.__new__(w2v.Word2VecModel)
+    torch.nn.Module.__init__(m)
+    m.word_embd = torch.nn.Embedding(sd["word_embd.weight"].shape[0], 300)
+    m.fc1 = torch.nn.Linear(300, 2048)
+    m.fc2 = torch.nn.Linear(2048, 512)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    tok = torch.from_numpy(ids)
+    out = m(input_ids=tok, attention_mask=(tok != 0))
+    pooled = out["pooler_output"]
+    g_out = torch.from_numpy(synth._normal("w2v.gout", 888, tuple(pooled.shape), 1.0))
+    (pooled * g_out).sum().backward()
+    res = {"pooler_output": pooled.detach().numpy(), "last_hidden_state": out["last_hidden_state"].detach().numpy()[:, ::8],
+           "in_checksum": np.array(sum(checksum(v) for v in sd.values()) + checksum(ids))}
+    for k, p in m.named_parameters():          # norm + every 97th element (word_embd is frozen: no gradient, :84-85)
+        if p.grad is None:
+            res["grad_none/" + k] = np.array(1)
+            continue
+        gflat = p.grad.detach().double().reshape(-1)
+        res["grad_norm/" + k] = np.array(float(gflat.norm()))
+        res["grad_sub/" + k] = gflat[::97].float().numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "g_word2vec.npz"), **res)
+    print("g_word2vec", pooled.shape, {k: float(v) for k, v in res.items() if k.startswith("grad_norm/")},
+          [k for k in res if k.startswith("grad_none/")])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -314,6 +373,8 @@ def main():
         run_bench_cases()
     if not a.only or a.only == "g_align":
         run_align()
+    if not a.only or a.only == "g_word2vec":
+        run_word2vec()
 
 
 if __name__ == "__main__":

@@ -262,6 +262,26 @@ class TanOracle:
 
 
 # ------------------------------------------------------------------------------------------------
+# Text embedder (model/word2vec_model.py:76-102)
+# ------------------------------------------------------------------------------------------------
+
+def word2vec_forward(sd, input_ids, attention_mask=None):
+    """Word2VecModel.forward: Embedding lookup -> fc1 + ReLU -> max over the words with ignored words at -6e4 (a
+    sentence without any kept word keeps all of them, :93) -> fc2.  Returns (pooler_output [S, 512],
+    last_hidden_state [S, W, 512])."""
+    x = _t(sd["word_embd.weight"])[torch.as_tensor(input_ids).long()]
+    x = torch.relu(x @ _t(sd["fc1.weight"]).t() + _t(sd["fc1.bias"]))
+    if attention_mask is not None:
+        keep = torch.as_tensor(attention_mask).bool().clone()
+        keep[keep.sum(-1) == 0, :] = True
+        pooled = x.masked_fill(~keep[:, :, None], -6e4).max(dim=1).values
+    else:
+        pooled = x.max(dim=1).values
+    w2, b2 = _t(sd["fc2.weight"]), _t(sd["fc2.bias"])
+    return pooled @ w2.t() + b2, x @ w2.t() + b2
+
+
+# ------------------------------------------------------------------------------------------------
 # Loss (train/loss.py)
 # ------------------------------------------------------------------------------------------------
 

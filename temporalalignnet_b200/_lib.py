@@ -17,7 +17,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 TAN_OK = 0
 ERR_NAMES = {-1: "TAN_ERR_SHAPE", -2: "TAN_ERR_ARCH", -3: "TAN_ERR_WORKSPACE", -4: "TAN_ERR_CUDA",
              -5: "TAN_ERR_ARG"}
-ACT_NONE, ACT_QUICKGELU = 0, 1
+ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
 ABI_VERSION = 4
 
 

@@ -16,7 +16,7 @@ extern "C" int tan_linear_bf16(const void* A, int64_t lda, const void* W, int64_
     return set_error(TAN_ERR_SHAPE, "tan_linear_bf16: need M>0, N>0, K%%64==0 (M=%d N=%d K=%d)", M, N, K);
   if (lda % 8 != 0 || ldw % 8 != 0 || lda < K || ldw < K)
     return set_error(TAN_ERR_SHAPE, "tan_linear_bf16: lda/ldw must be >= K and multiples of 8");
-  if (act != TAN_ACT_NONE && act != TAN_ACT_QUICKGELU) return set_error(TAN_ERR_ARG, "tan_linear_bf16: bad act");
+  if (act != TAN_ACT_NONE && act != TAN_ACT_QUICKGELU && act != TAN_ACT_RELU) return set_error(TAN_ERR_ARG, "tan_linear_bf16: bad act");
   if (N % 128 != 0)
     return set_error(TAN_ERR_SHAPE, "tan_linear_bf16: N (output features) must be a multiple of 128 (N=%d)", N);
   if (residual != nullptr && out_f32 == nullptr)

@@ -100,6 +100,7 @@ struct LinearEpi2 {
           float a0 = __uint_as_float(rc[4 * j]) + b.x, a1 = __uint_as_float(rc[4 * j + 1]) + b.y;
           float a2 = __uint_as_float(rc[4 * j + 2]) + b.z, a3 = __uint_as_float(rc[4 * j + 3]) + b.w;
           if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
+          else if (act == TAN_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
           *reinterpret_cast<float4*>(buf + swz128(lane, j)) = make_float4(a0, a1, a2, a3);
         }
         __syncwarp();
@@ -134,6 +135,7 @@ struct LinearEpi2 {
           float a0 = __uint_as_float(rc[4 * j]) + b.x, a1 = __uint_as_float(rc[4 * j + 1]) + b.y;
           float a2 = __uint_as_float(rc[4 * j + 2]) + b.z, a3 = __uint_as_float(rc[4 * j + 3]) + b.w;
           if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
+          else if (act == TAN_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
           packed[2 * j] = pack_bf16x2(a0, a1);
           packed[2 * j + 1] = pack_bf16x2(a2, a3);
         }

@@ -146,12 +146,18 @@ def padded_times(start_list, end_list, T: int, N: int, device):
 
 
 def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, device, shard: bool,
-                       pos_fn=None) -> NceInputs:
+                       pos_fn=None, padded=None) -> NceInputs:
     """Targets of the `--model init` recipe: bit (b, t, n) = real sentence and start <= t < end
     (train/loss.py:26-41,:80-85), built on the device by tan_pos_from_time; the column-valid mask
     (~text_padding_mask, :235) is all-gathered over ranks with `shard` so that columns are global."""
     B = len(start_list)
-    start, end = padded_times(start_list, end_list, T, N, device)
+    if padded is not None:                      # data.collate_fn already padded the times (pinned -> one async copy)
+        start, end = (t.to(device, non_blocking=True).float() for t in padded)
+        if start.shape[1] < N:                  # sharded runs pad the text to the longest N of any rank
+            start = torch.nn.functional.pad(start, (0, N - start.shape[1]), value=float(T) + 1e2)
+            end = torch.nn.functional.pad(end, (0, N - end.shape[1]), value=-1e2)
+    else:
+        start, end = padded_times(start_list, end_list, T, N, device)
     valid = (~text_padding_mask.to(device).bool()).to(torch.uint8).contiguous()
     pos_fn = ops.pos_from_time if pos_fn is None else pos_fn      # (tests inject a torch checker on CPU)
     posbits = pos_fn(start.contiguous(), end.contiguous(), valid, B, T, N)
@@ -261,14 +267,16 @@ def pack_text_features(td: torch.Tensor, tj: torch.Tensor) -> torch.Tensor:
     return torch.cat((td[None], tj), dim=0).contiguous()
 
 
-_COALESCE = os.environ.get("TAN_GATHER_COALESCED", "1") != "0"
+# measured on 2 x B200 (profiles/r02f): the exchange alone takes 0.18 ms as one all-gather + permuting copy and 0.62 ms
+# as a coalesced group of per-stage all-gathers that write the stage-major layout directly -- so the group is opt-in
+_COALESCE = os.environ.get("TAN_GATHER_COALESCED", "0") == "1"
 
 
 def exchange_text_features(packed: torch.Tensor, dist) -> torch.Tensor:
     """The one exchange step of the path: [1 + Sj, B_loc*N, d] per rank -> stage-major
     [1 + Sj, W*B_loc*N, d] (global column c = rank * B_loc*N + local column), the layout the similarity kernel's 2-D
-    TMA map reads.  One coalesced NCCL launch of per-stage all-gathers writes that layout directly; the fallback is
-    one all-gather into a rank-major buffer + a permuting copy."""
+    TMA map reads: one all-gather into a rank-major buffer + a permuting copy (or, TAN_GATHER_COALESCED=1, a
+    coalesced group of per-stage all-gathers that writes the layout directly; measured slower)."""
     W = dist.get_world_size()
     S1, BN, d = packed.shape
     full = torch.empty(S1, W * BN, d, dtype=packed.dtype, device=packed.device)
@@ -423,7 +431,8 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
                            f"B {b_min}..{b_max}, N {n_min}..{n_max}).  Pad the text inputs with "
                            "temporalalignnet_b200.loss.pad_text_to_global(lang_embed, lang_padding_mask) before the "
                            "forward, and give every rank the same number of clips.")
-    nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard)
+    padded = (input_data['start_pad'], input_data['end_pad']) if 'start_pad' in input_data else None
+    nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard, padded=padded)
     loss_dict = {}
     # training step: the forward ran with a tape (model.enable_autograd) -> the returned loss carries ONE autograd
     # node whose backward is the hand-written backward pass (train.py)

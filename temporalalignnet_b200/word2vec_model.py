@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import TanError
+from ._lib import ACT_RELU, TanError
 from .tfm_model import _Bf16Cache, _f32
 
 MAX_WORDS = 32          # model/word2vec_model.py:28 (Word2VecTokenizer pads / cuts every sentence to 32 words)
@@ -34,7 +34,7 @@ class _TextEmbedFn(torch.autograd.Function):
     def forward(ctx, module, x_tok, keep_u8, S, w1, b1, w2, b2):
         c = module._cache
         w1p = module._w1_padded()
-        pooled, arg = ops.text_pool_fc1(x_tok, w1p, _f32(b1), keep_u8, S, want_argmax=torch.is_grad_enabled() or True)
+        pooled, arg = ops.text_pool_fc1(x_tok, w1p, _f32(b1), keep_u8, S, want_argmax=True)
         out = torch.empty(S, w2.shape[0], dtype=torch.float32, device=x_tok.device)
         ops.linear(pooled, c.get(w2), _f32(b2), out_f32=out, tag="text_embed")
         ctx.module, ctx.S = module, S
@@ -133,7 +133,7 @@ class Word2VecModel(nn.Module):
         if self.want_last_hidden_state:       # fc2(relu(fc1(x))) of every word (:98): not read by TAN
             with torch.no_grad():
                 h = torch.empty(S * MAX_WORDS, self.fc1.weight.shape[0], dtype=torch.bfloat16, device=ids.device)
-                ops.linear(x_tok, self._w1_padded(), _f32(self.fc1.bias), out_bf16=h, act=2, tag="text_embed")
+                ops.linear(x_tok, self._w1_padded(), _f32(self.fc1.bias), out_bf16=h, act=ACT_RELU, tag="text_embed")
                 last = torch.empty(S * MAX_WORDS, self.fc2.weight.shape[0], dtype=torch.float32, device=ids.device)
                 ops.linear(h, self._cache.get(self.fc2.weight), _f32(self.fc2.bias), out_f32=last, tag="text_embed")
                 out['last_hidden_state'] = last.view(S, MAX_WORDS, -1)[:, :W]

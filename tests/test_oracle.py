@@ -283,3 +283,24 @@ def test_eager_port_matches_oracle_on_cpu():
     assert max_abs(out["logits_joint"], ref["logits_joint"]) < FP32_TOL
     for k in ("loss", "loss-dual", "loss-joint"):
         assert abs(float(loss[k]) - float(ref_loss[k])) < 1e-5 * abs(float(ref_loss[k])), k
+
+
+def test_oracle_word2vec_vs_reference_fixture():
+    """g_word2vec.npz: Word2VecModel.forward (model/word2vec_model.py:83-101) of the reference on synthetic weights,
+    incl. an all-stop-word sentence (:93) and a repeated word; oracle forward + autograd against it."""
+    from oracle.make_golden import make_word2vec_case
+    g = load_golden("g_word2vec")
+    sd, ids = make_word2vec_case()
+    assert abs(sum(checksum(v) for v in sd.values()) + checksum(ids) - float(g["in_checksum"])) < 1e-6
+    leaves = {k: torch.from_numpy(v).clone().requires_grad_(k != "word_embd.weight") for k, v in sd.items()}
+    tok = torch.from_numpy(ids)
+    pooled, last = O.word2vec_forward(leaves, tok, tok != 0)
+    assert max_abs(pooled.detach(), g["pooler_output"]) < 1e-4
+    assert max_abs(last.detach()[:, ::8], g["last_hidden_state"]) < 1e-4
+    g_out = torch.from_numpy(synth._normal("w2v.gout", 888, tuple(pooled.shape), 1.0))
+    (pooled * g_out).sum().backward()
+    assert "grad_none/word_embd.weight" in g
+    for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"):
+        got = leaves[k].grad.double().reshape(-1)
+        assert abs(float(got.norm()) - float(g["grad_norm/" + k])) < 1e-4 * float(g["grad_norm/" + k]), k
+        assert max_abs(got[::97], g["grad_sub/" + k]) < 1e-4 * max(1.0, float(np.abs(g["grad_sub/" + k]).max())), k
