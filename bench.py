@@ -418,13 +418,16 @@ def run_gpu_arm(args):
     s_ = agg["sim_nce_fwd"]
     fl = runner.flops_per_clip()
     # useful flops of the similarity: only real sentences are columns of the reference's matrix (it drops the padded
-    # ones before the loss, train/loss.py:235); the kernel also computes the padded columns
-    col_frac = float(runner.nce.col_valid.float().mean().item())
+    # ones before the loss, train/loss.py:235).  With ragged columns (default) the kernel computes exactly those and
+    # `achieved` counts only them; without, it also computes the padded columns
+    nce_ = runner.nce
+    col_frac = 1.0 if nce_.compact else float(nce_.col_valid.float().mean().item())
     extra["roofline_sim"] = {"kernel": "sim_fused_kernel + sim_reduce_partials_kernel (tan_sim_nce_fwd, fused mode: "
                                        "the logits never reach HBM)", "bound": "tensor",
                              "achieved": round(s_[0] / (s_[1] * 1e-3) / 1e12, 1), "peak": tf_peak,
                              "unit": "TFLOP/s", "frac": round(s_[0] / (s_[1] * 1e-3) / 1e12 / tf_peak, 4),
-                             "valid_column_fraction": round(col_frac, 4),
+                             "ragged_columns": bool(nce_.compact), "columns_computed": int(nce_.C),
+                             "columns_padded_layout": int(nce_.C_pad), "valid_column_fraction": round(col_frac, 4),
                              "frac_useful": round(col_frac * s_[0] / (s_[1] * 1e-3) / 1e12 / tf_peak, 4),
                              "traffic": (traffic.get("sim_nce_fwd") or {}).get("bytes_per_launch") if default_shape else None,
                              "columns": "local rows x GLOBAL columns (text features pre-gathered outside the class graph)"}
@@ -721,7 +724,9 @@ def hbm_nce_roofline(runner, peaks, flush):
         rs = torch.empty(2, B * S * T, dtype=torch.float32, device=dense.device)
         cs = torch.empty(2, S, B2 * N, dtype=torch.float32, device=dense.device)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dense.device)
-        nce = runner.nce
+        # materialised logits keep the padded [B, S, T, B, N] layout: targets without the ragged-column compaction
+        nce = loss_mod.prepare_nce_inputs(runner.batch["start"], runner.batch["end"], runner.d_tpm, runner.T, runner.N,
+                                          runner.device, False, compact=False)
         ts = []
         for i in range(8):
             flush.zero_()

@@ -45,6 +45,7 @@ extern "C" {
 #define TAN_ACT_NONE 0
 #define TAN_ACT_QUICKGELU 1 /* x * sigmoid(1.702 x), model/tfm_model.py:11-13 */
 #define TAN_ACT_RELU 2      /* max(x, 0), model/word2vec_model.py:86 */
+#define TAN_ACT_QUICKGELU_GRAD 3 /* internal to tan_linear_gelu_bwd_bf16: multiply by d QuickGELU / dx of a second operand */
 
 /* ---- library ------------------------------------------------------------------------------- */
 
@@ -82,6 +83,18 @@ TAN_API int tan_cast_f32_to_bf16(const float* in, void* out, size_t n, void* str
 TAN_API int tan_linear_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                     const float* residual, int64_t ldr, float* out_f32, int64_t ldo_f32,
                     void* out_bf16, int64_t ldo_bf16, int M, int N, int K, int act, void* stream);
+
+/* Training forward of c_fc: out_act = act(A W^T + bias) and out_pre = A W^T + bias (both bf16 [M, N]) from ONE GEMM --
+ * QuickGELU's backward needs the pre-activation, the next GEMM the activation (model/tfm_model.py:23-25,:37).  Same
+ * operand requirements as tan_linear_bf16. */
+TAN_API int tan_linear_dual_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                 void* out_act, int64_t ldo_act, void* out_pre, int64_t ldo_pre, int M, int N, int K,
+                                 int act, void* stream);
+
+/* Backward through c_proj and QuickGELU in one GEMM: out = (A W^T) o gelu'(u), bf16 [M, N]; u [M, N] bf16 (ldu) are the
+ * pre-activations stored by tan_linear_dual_bf16 (autograd of model/tfm_model.py:11-13,:37). */
+TAN_API int tan_linear_gelu_bwd_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* u, int64_t ldu,
+                                     void* out, int64_t ldo, int M, int N, int K, void* stream);
 
 /* Fused projection + residual + LayerNorm for an output width of 512 (= the model width):
  *     x   <- x + A @ W^T + bias                 x [M, 512] fp32 (ldx), updated in place
@@ -183,10 +196,16 @@ typedef struct tan_sim_geom {
   int B_loc;   /* local clips (rows) */
   int S;       /* stages */
   int T;       /* frames per clip */
-  int C;       /* global text columns = B_glob * N */
-  int N;       /* sentences per clip (padded) */
+  int C;       /* global text columns: B_glob * N, or col_off[B_glob] with ragged columns */
+  int N;       /* sentences per clip (padded): bits per target row */
   int d;       /* feature width */
   int b_off;   /* global index of local clip 0 */
+  /* Ragged ("compact") columns, optional (NULL = every clip owns N columns): device array [B_glob + 1] of prefix
+   * offsets, clip b' owns columns [col_off[b'], col_off[b' + 1]) and its sentence n is column col_off[b'] + n.
+   * The reference drops padded sentences before the loss (train/loss.py:235); with this layout they are never
+   * computed at all (25 % of the columns at BASELINE's n_b ~ U[N/2, N]).  Not available with materialised logits
+   * (logits_out / tan_nce_from_logits keep the [B, S, T, B, N] layout). */
+  const int32_t* col_off;
 } tan_sim_geom;
 
 /* Targets.  posbits [B_loc, T, W] uint32, W = ceil(N / 32): bit (n % 32) of word n / 32 of posbits[b][t] is

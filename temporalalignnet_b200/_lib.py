@@ -42,7 +42,7 @@ class LnArgs(C.Structure):
 class SimGeom(C.Structure):
     """struct tan_sim_geom (include/tan_b200.h)."""
     _fields_ = [("B_loc", C.c_int), ("S", C.c_int), ("T", C.c_int), ("C", C.c_int), ("N", C.c_int),
-                ("d", C.c_int), ("b_off", C.c_int)]
+                ("d", C.c_int), ("b_off", C.c_int), ("col_off", C.c_void_p)]
 
 
 class OptimTensor(C.Structure):
@@ -61,6 +61,10 @@ SIGNATURES = {
     "tan_linear_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p]),
+    "tan_linear_dual_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tan_linear_gelu_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tan_linear_res_ln_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p]),

@@ -569,6 +569,8 @@ extern "C" int tan_sim_grad_tiles(const float* z, int64_t ldz, int Rc, int Rc_pa
                                   const float* ra, const float* rap, const float* cb, const float* cbp, void* G,
                                   int64_t ldg, void* GT, int64_t ldgt, void* stream) {
   TAN_CHECK(tan_device_check());
+  if (g != nullptr && g->col_off != nullptr)
+    return set_error(TAN_ERR_ARG, "tan_sim_grad_tiles: ragged columns (col_off) are only supported by tan_sim_grad_gemm");
   if (z == nullptr || g == nullptr || posbits == nullptr || col_valid == nullptr || ra == nullptr || rap == nullptr ||
       cb == nullptr || cbp == nullptr || G == nullptr || GT == nullptr)
     return set_error(TAN_ERR_ARG, "tan_sim_grad_tiles: null pointer");

@@ -18,6 +18,13 @@ namespace tanb {
 // The accumulator itself leaves TMEM at ~64 B/clk/SM (1.05 us per tile), which is the floor of any epilogue.
 constexpr int kModeBf16 = 0;   // out_bf16 only
 constexpr int kModeF32 = 1;    // out_f32 (+ residual) (+ bf16 copy)
+constexpr int kModeBf16Dual = 2;   // out_bf16 = act(x) AND a second bf16 output with the pre-activation x (training tape)
+
+// d/dx [x sigmoid(1.702 x)] = s + 1.702 x s (1 - s),  s = sigmoid(1.702 x) = 0.5 (1 + tanh(0.851 x))
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  const float sg = 0.5f * (1.0f + fast_tanh(0.851f * x));
+  return sg * (1.0f + 1.702f * x * (1.0f - sg));
+}
 
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
@@ -26,8 +33,9 @@ struct LinearEpi2 {
   // Ring depth over staging space: the MMA warp trails the TMA producer by a constant ~1.8 us (per-CTA timelines,
   // tan_debug_set_trace), so bytes in flight pace these GEMMs: the epilogue keeps ONE 4 KB staging box per warp
   // and the ring gets 6 stages (192 KB in flight per SM): +8 % over 4 stages on the K = 512 layers (same box).
-  static constexpr int kStages = 6;
-  static constexpr int kWarpScratch = 4096;
+  // (the dual-output mode needs a second staging box per warp and gives up one ring stage for it)
+  static constexpr int kStages = MODE == kModeBf16Dual ? 5 : 6;
+  static constexpr int kWarpScratch = MODE == kModeBf16Dual ? 8192 : 4096;
   struct State {
     float4 res[8];         // kModeF32: residual of the next chunk, lane = (row % 4, 16-byte column)
   };
@@ -40,8 +48,8 @@ struct LinearEpi2 {
   int64_t ldr;
   float* out_f32;
   int64_t ldo;
-  bf16* extra_bf16;        // kModeF32 only: optional second output
-  int64_t ld_extra;
+  bf16* extra_bf16;        // kModeF32: optional second output (bf16 copy).  kModeBf16 with act == TAN_ACT_QUICKGELU_GRAD:
+  int64_t ld_extra;        // the pre-activations u [M, N] the result is multiplied with gelu'(u) of (read-only)
 
   __device__ __forceinline__ int num_tiles() const { return n_tiles; }
   // feature tiles fastest: concurrently resident pair tiles share token rows (A) and cover all of W
@@ -76,7 +84,7 @@ struct LinearEpi2 {
 
   __device__ __forceinline__ void run(int tile, uint32_t rank, uint32_t tmem_acc, int ew, int lane, uint8_t* ws,
                                       const float* colvec, uint64_t*, uint32_t, const CUtensorMap* tmOut,
-                                      const CUtensorMap*, State& st) const {
+                                      const CUtensorMap* tmAux, State& st) const {
     const int quarter = ew & 3, half = ew >> 2;
     const int row0 = (tile / f_tiles) * (2 * kG2BM) + static_cast<int>(rank) * kG2BM + quarter * 32;
     const int col0 = (tile % f_tiles) * kG2BN + half * 128;
@@ -129,13 +137,32 @@ struct LinearEpi2 {
         if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const uint32_t(&rc)[32] = r[c & 1];
         uint32_t packed[16];
+        uint32_t packed_u[MODE == kModeBf16Dual ? 16 : 1];
+        uint4 uu[4];                                    // QUICKGELU_GRAD: this row's 32 pre-activations of the chunk
+        const bool mul_grad = MODE == kModeBf16 && act == TAN_ACT_QUICKGELU_GRAD;
+        if (mul_grad) {
+          const bool ok = row0 + lane < M && col0 + 32 * c < N;
+          const uint4* pu = reinterpret_cast<const uint4*>(extra_bf16 + static_cast<int64_t>(row0 + lane) * ld_extra + col0 + 32 * c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) uu[j] = ok ? __ldg(pu + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b = bvec[c * 8 + j];
           float a0 = __uint_as_float(rc[4 * j]) + b.x, a1 = __uint_as_float(rc[4 * j + 1]) + b.y;
           float a2 = __uint_as_float(rc[4 * j + 2]) + b.z, a3 = __uint_as_float(rc[4 * j + 3]) + b.w;
+          if (MODE == kModeBf16Dual) {
+            packed_u[2 * j] = pack_bf16x2(a0, a1);
+            packed_u[2 * j + 1] = pack_bf16x2(a2, a3);
+          }
           if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
           else if (act == TAN_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          else if (mul_grad) {
+            const uint4 q = uu[j >> 1];
+            const float2 u01 = unpack_bf16x2((j & 1) ? q.z : q.x), u23 = unpack_bf16x2((j & 1) ? q.w : q.y);
+            a0 *= quick_gelu_grad(u01.x); a1 *= quick_gelu_grad(u01.y);
+            a2 *= quick_gelu_grad(u23.x); a3 *= quick_gelu_grad(u23.y);
+          }
           packed[2 * j] = pack_bf16x2(a0, a1);
           packed[2 * j + 1] = pack_bf16x2(a2, a3);
         }
@@ -145,14 +172,19 @@ struct LinearEpi2 {
         }
         // 32 features = 64 bytes = chunks [4 * (c & 1), +4) of this row of the [32 x 64] bf16 box
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
           *reinterpret_cast<uint4*>(ws + swz128(lane, 4 * (c & 1) + j)) =
               make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          if (MODE == kModeBf16Dual)
+            *reinterpret_cast<uint4*>(ws + 4096 + swz128(lane, 4 * (c & 1) + j)) =
+                make_uint4(packed_u[4 * j], packed_u[4 * j + 1], packed_u[4 * j + 2], packed_u[4 * j + 3]);
+        }
         if (c & 1) {                                    // box complete: 64 features of 32 tokens
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && row0 < M && col0 + 32 * (c - 1) < N) {
             tma_store_2d(tmOut, ws, col0 + 32 * (c - 1), row0);
+            if (MODE == kModeBf16Dual) tma_store_2d(tmAux, ws + 4096, col0 + 32 * (c - 1), row0);
             tma_store_commit();
           }
         }

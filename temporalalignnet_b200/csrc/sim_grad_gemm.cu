@@ -22,7 +22,7 @@ struct SimGradEpi {
   static constexpr int kWarpScratch = 5120;
   struct State {
     float a, ap;           // row coefficients
-    int own0;              // first column of the row's own clip
+    int own0, own_n;       // first column / number of columns of the row's own clip
     uint32_t bits[2];      // the row's target bits (N <= 64)
     int kill;
   };
@@ -37,6 +37,7 @@ struct SimGradEpi {
   const uint8_t* col_valid;
   const uint8_t* row_kill;
   const uint32_t* posbits;
+  const int32_t* col_off;  // ragged columns (tan_sim_geom.col_off) or NULL
 
   __device__ __forceinline__ int num_tiles() const { return n_tiles; }
   __device__ __forceinline__ PairTile coord(int tile) const {
@@ -59,13 +60,19 @@ struct SimGradEpi {
     vec(ws, ew, 1)[et] = ok ? __ldg(cb + c) : 0.f;
     vec(ws, ew, 2)[et] = ok ? __ldg(cbp + c) : 0.f;
     const int rl = (tile / f_tiles) * (2 * kG2BM) + static_cast<int>(rank) * kG2BM + (ew & 3) * 32 + lane;
-    st.a = 0.f; st.ap = 0.f; st.own0 = 0; st.bits[0] = 0; st.bits[1] = 0; st.kill = 0;
+    st.a = 0.f; st.ap = 0.f; st.own0 = 0; st.own_n = 0; st.bits[0] = 0; st.bits[1] = 0; st.kill = 0;
     if (rl < M) {
       const int r = r0 + rl;
       const int b = r / T, t = r - b * T;
       st.a = __ldg(ra + r);
       st.ap = __ldg(rap + r);
-      st.own0 = (b_off + b) * Ns;
+      if (col_off != nullptr) {
+        st.own0 = __ldg(col_off + b_off + b);
+        st.own_n = __ldg(col_off + b_off + b + 1) - st.own0;
+      } else {
+        st.own0 = (b_off + b) * Ns;
+        st.own_n = Ns;
+      }
       const uint32_t* pw = posbits + (static_cast<int64_t>(b) * T + t) * W;
       st.bits[0] = pw[0];
       st.bits[1] = W > 1 ? pw[1] : 0u;
@@ -103,11 +110,11 @@ struct SimGradEpi {
       }
       // the row's own clip: positives subtract their (rap + cbp) share, killed frames lose the block
       const int n_lo = col0 + 32 * c - st.own0;              // sentence index of this chunk's first column
-      if (n_lo + 32 > 0 && n_lo < Ns) {
+      if (n_lo + 32 > 0 && n_lo < st.own_n) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n_lo + j;
-          if (n >= 0 && n < Ns) {
+          if (n >= 0 && n < st.own_n) {
             if (st.kill) {
               g[j] = 0.f;
             } else if ((((n >> 5) ? st.bits[1] : st.bits[0]) >> (n & 31)) & 1u) {
@@ -169,6 +176,7 @@ extern "C" int tan_sim_grad_gemm(const void* vfeat, int64_t ldv, const void* tfe
   e.n_tiles = e.f_tiles * ((Rc + 2 * kG2BM - 1) / (2 * kG2BM));
   e.r0 = r0; e.T = g->T; e.Ns = g->N; e.W = (g->N + 31) / 32; e.b_off = g->b_off;
   e.ra = ra; e.rap = rap; e.cb = cb; e.cbp = cbp; e.col_valid = col_valid; e.row_kill = row_kill; e.posbits = posbits;
+  e.col_off = g->col_off;
   CUtensorMap tmA, tmB, tmOut;
   TAN_CHECK(make_tmap_2d(&tmA, vfeat, 2, Rc, K, ldv, kG2BM));
   TAN_CHECK(make_tmap_2d(&tmB, tfeat, 2, C_pad, K, ldt, kG2BN / 2));

@@ -41,6 +41,17 @@ struct SimCommon {
   int64_t R;                 // B_loc * S * T
 };
 
+// Columns [c0, c1) of local clip b_loc's own sentences (sentence n = column c0 + n).
+__device__ __forceinline__ void own_columns(const tan_sim_geom& g, int b_loc, int& c0, int& c1) {
+  if (g.col_off != nullptr) {
+    c0 = __ldg(g.col_off + g.b_off + b_loc);
+    c1 = __ldg(g.col_off + g.b_off + b_loc + 1);
+  } else {
+    c0 = (g.b_off + b_loc) * g.N;
+    c1 = c0 + g.N;
+  }
+}
+
 // 32 target bits of one frame for sentences n0 .. n0+31 of its clip (n0 in (-32, N); sentences < 0 give 0).
 __device__ __forceinline__ uint32_t pos_bits32(const uint32_t* __restrict__ pw, int W, int n0) {
   if (n0 >= 0) {
@@ -292,9 +303,8 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       x.all_rows = __all_sync(0xffffffffu, x.row_ok);
       x.kill = c.row_kill != nullptr && x.row_ok && c.row_kill[b_loc * c.g.T + t] != 0;
       x.any_kill = __any_sync(0xffffffffu, x.kill);
-      x.pos_c0 = (c.g.b_off + b_loc) * c.g.N;
-      x.pos_c1 = x.pos_c0 + c.g.N;
-      x.N = c.g.N;
+      own_columns(c.g, b_loc, x.pos_c0, x.pos_c1);
+      x.N = x.pos_c1 - x.pos_c0;
       x.W = c.W;
       x.pw = c.posbits + (static_cast<int64_t>(b_loc) * c.g.T + (x.row_ok ? t : 0)) * c.W;
       const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
@@ -444,9 +454,8 @@ struct SimEpi2 {
     x.all_rows = __all_sync(0xffffffffu, x.row_ok);
     x.kill = c.row_kill != nullptr && x.row_ok && c.row_kill[b_loc * c.g.T + t] != 0;
     x.any_kill = __any_sync(0xffffffffu, x.kill);
-    x.pos_c0 = (c.g.b_off + b_loc) * c.g.N;
-    x.pos_c1 = x.pos_c0 + c.g.N;
-    x.N = c.g.N;
+    own_columns(c.g, b_loc, x.pos_c0, x.pos_c1);
+    x.N = x.pos_c1 - x.pos_c0;
     x.W = c.W;
     x.pw = c.posbits + (static_cast<int64_t>(b_loc) * c.g.T + (x.row_ok ? t : 0)) * c.W;
     const int64_t r = static_cast<int64_t>(seg) * c.g.T + t;
@@ -684,7 +693,8 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, int clips_p
   const int b_begin = chunk * clips_per_cta, b_end = min(b_begin + clips_per_cta, c.g.B_loc);
   for (int b = b_begin; b < b_end; ++b) {
     const int seg = b * c.g.S + s_idx;
-    const int pos_c0 = (c.g.b_off + b) * c.g.N, pos_c1 = pos_c0 + c.g.N;
+    int pos_c0, pos_c1;
+    own_columns(c.g, b, pos_c0, pos_c1);
     const bool slab_has_pos = slab * kNceCols < pos_c1 && (slab + 1) * kNceCols > pos_c0;   // CTA-uniform
     const bool lane_has_pos = col0 < pos_c1 && col0 + 8 > pos_c0;
     const bool has_kill = c.row_kill != nullptr;
@@ -763,7 +773,7 @@ nce_from_logits_kernel(const void* __restrict__ logits, SimCommon c, int clips_p
           if (has_kill && c.row_kill[b * c.g.T + t] != 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              killmask |= (static_cast<unsigned>(j + n0) < static_cast<unsigned>(c.g.N)) ? (1u << j) : 0u;
+              killmask |= (static_cast<unsigned>(j + n0) < static_cast<unsigned>(pos_c1 - pos_c0)) ? (1u << j) : 0u;
           }
         }
         const uint32_t live = row_ok ? (okbits & ~killmask) : 0u;
@@ -833,7 +843,9 @@ __global__ void pos_from_time_kernel(const float* __restrict__ start, const floa
 __global__ void nce_reduce_kernel(const float* __restrict__ row_sums, int64_t R, int S, int T,
                                   const uint8_t* __restrict__ row_sel, const float* __restrict__ col_sums, int64_t SC,
                                   int C, const uint8_t* __restrict__ col_sel, double* __restrict__ out) {
-  // fp64 accumulation: the cross-block atomic order then only perturbs bits far below fp32 epsilon
+  // Deterministic although the blocks combine through atomics: every block's fp64 partial is rounded to a multiple
+  // of 2^-20 before it is added, so all additions are EXACT in fp64 (|sum| < 2^22, <= 2^10 blocks: 52 bits) and
+  // their order cannot change the result (the rounding moves the loss by < 1e-9 relative)
   double acc[4] = {0., 0., 0., 0.};
   pdl_launch_dependents();
   pdl_wait();
@@ -874,6 +886,7 @@ __global__ void nce_reduce_kernel(const float* __restrict__ row_sums, int64_t R,
       double v = lane < (blockDim.x >> 5) ? sred[k][lane] : 0.;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((k & 1) == 0) v = rint(v * 1048576.0) * (1.0 / 1048576.0);
       if (lane == 0 && v != 0.) atomicAdd(out + k, v);
     }
   }
@@ -884,7 +897,7 @@ static int fill_common(SimCommon* c, const tan_sim_geom* g, const uint32_t* posb
   if (g == nullptr || posbits == nullptr || col_valid == nullptr)
     return set_error(TAN_ERR_ARG, "sim/nce: null geometry, target-bit or column-mask pointer");
   if (g->B_loc <= 0 || g->S <= 0 || g->T <= 0 || g->C <= 0 || g->N <= 0 || g->d <= 0 || g->b_off < 0 ||
-      g->C % g->N != 0 || (g->b_off + g->B_loc) * static_cast<int64_t>(g->N) > g->C)
+      (g->col_off == nullptr && (g->C % g->N != 0 || (g->b_off + g->B_loc) * static_cast<int64_t>(g->N) > g->C)))
     return set_error(TAN_ERR_SHAPE, "sim/nce: bad geometry B_loc=%d S=%d T=%d C=%d N=%d d=%d b_off=%d", g->B_loc, g->S,
                      g->T, g->C, g->N, g->d, g->b_off);
   c->g = *g;

@@ -120,11 +120,58 @@ def pad_text_to_global(lang_embed: torch.Tensor, lang_padding_mask: torch.Tensor
 
 class NceInputs:
     """Device-side description of the targets: packed positive bits of the LOCAL clips [B_loc, T, W] and the
-    column-valid mask over the GLOBAL columns; optional row_kill / row_sel / col_sel (see include/tan_b200.h)."""
+    column-valid mask over the GLOBAL columns; optional row_kill / row_sel / col_sel (see include/tan_b200.h).
 
-    def __init__(self, posbits, col_valid, N, T, b_off, B_glob, row_kill=None, row_sel=None, col_sel=None):
+    Ragged ("compact") columns: the reference drops the padded sentences before the loss (train/loss.py:235); with
+    `col_off` set, the similarity kernels never compute them.  `col_src` [C] maps every compact column to its column
+    in the padded [B_glob, N] layout (the layout of the text features), `col_valid` is already compact, `C_pad` =
+    B_glob * N.  The lengths come from the HOST lists (`input_data['start']`), like the reference's own padding mask
+    (train/main.py:52,:62-65); `poison` is a device flag set when the padding mask marks a sentence BEYOND a clip's
+    list length as real -- the compact layout would silently drop it, so the loss is turned into NaN instead."""
+
+    def __init__(self, posbits, col_valid, N, T, b_off, B_glob, row_kill=None, row_sel=None, col_sel=None,
+                 col_off=None, col_src=None, poison=None):
         self.posbits, self.col_valid, self.N, self.T, self.b_off, self.B_glob = posbits, col_valid, N, T, b_off, B_glob
         self.row_kill, self.row_sel, self.col_sel = row_kill, row_sel, col_sel
+        self.col_off, self.col_src, self.poison = col_off, col_src, poison
+        self.C_pad = B_glob * N
+        self._stage_ids = {}
+
+    @property
+    def compact(self) -> bool:
+        return self.col_off is not None
+
+    @property
+    def C(self) -> int:
+        return int(self.col_src.numel()) if self.compact else self.C_pad
+
+    def geom(self, B_loc, S, T, d):
+        return ops.sim_geom(B_loc, S, T, self.C, self.N, d, self.b_off, col_off=self.col_off)
+
+    def compact_features(self, tfeat: torch.Tensor) -> torch.Tensor:
+        """[C_pad, d] -> [C, d] or [S, C_pad, d] -> [S, C, d] (bf16 rows gathered by tan_embed_gather_bf16)."""
+        if not self.compact:
+            return tfeat
+        d = tfeat.shape[-1]
+        S = 1 if tfeat.dim() == 2 else tfeat.shape[0]
+        ids = self._stage_ids.get(S)
+        if ids is None:
+            ids = (torch.arange(S, device=self.col_src.device, dtype=torch.int64)[:, None] * self.C_pad +
+                   self.col_src[None]).reshape(-1).contiguous()
+            self._stage_ids[S] = ids
+        out = ops.embed_gather(ids, tfeat.reshape(S * self.C_pad, d).contiguous())
+        return out.view(self.C, d) if tfeat.dim() == 2 else out.view(S, self.C, d)
+
+    def scatter_columns(self, x: torch.Tensor) -> torch.Tensor:
+        """[S, >= C, d] over compact columns -> [S, C_pad, d] over padded columns (zeros at padded sentences)."""
+        if not self.compact:
+            return x
+        out = torch.zeros(x.shape[0], self.C_pad, x.shape[2], dtype=x.dtype, device=x.device)
+        out.index_copy_(1, self.col_src, x[:, :self.C])
+        return out
+
+    def guard(self, loss: torch.Tensor) -> torch.Tensor:
+        return loss if self.poison is None else torch.where(self.poison, torch.full_like(loss, float("nan")), loss)
 
 
 def padded_times(start_list, end_list, T: int, N: int, device):
@@ -145,11 +192,35 @@ def padded_times(start_list, end_list, T: int, N: int, device):
     return dev[0], dev[1]
 
 
+COMPACT_COLUMNS = os.environ.get("TAN_COMPACT_COLUMNS", "1") != "0"
+
+
+def _host_all_gather_int(vec, device):
+    """All-gather a short list of ints over the ranks through a SIDE stream (see shard_shapes) -> flat python list."""
+    dist = _dist()
+    device = torch.device(device)
+    t = torch.tensor(vec, dtype=torch.int64)
+    W = dist.get_world_size()
+    st = _shape_streams.get(str(device))
+    if st is None:
+        st = _shape_streams[str(device)] = torch.cuda.Stream(device=device) if device.type == "cuda" else False
+    if st:
+        with torch.cuda.stream(st):
+            td = t.to(device, non_blocking=True)
+            out = torch.empty(W * td.numel(), dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(out, td)
+            return out.cpu().tolist()
+    outs = [torch.empty_like(t) for _ in range(W)]
+    dist.all_gather(outs, t)
+    return torch.cat(outs).tolist()
+
+
 def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, device, shard: bool,
-                       pos_fn=None, padded=None) -> NceInputs:
+                       pos_fn=None, padded=None, compact: bool = False) -> NceInputs:
     """Targets of the `--model init` recipe: bit (b, t, n) = real sentence and start <= t < end
     (train/loss.py:26-41,:80-85), built on the device by tan_pos_from_time; the column-valid mask
-    (~text_padding_mask, :235) is all-gathered over ranks with `shard` so that columns are global."""
+    (~text_padding_mask, :235) is all-gathered over ranks with `shard` so that columns are global.
+    compact: ragged columns from the host-side sentence counts (see NceInputs)."""
     B = len(start_list)
     if padded is not None:                      # data.collate_fn already padded the times (pinned -> one async copy)
         start, end = (t.to(device, non_blocking=True).float() for t in padded)
@@ -163,11 +234,32 @@ def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, 
     posbits = pos_fn(start.contiguous(), end.contiguous(), valid, B, T, N)
     dist = _dist() if shard else None
     if dist is None:
-        return NceInputs(posbits, valid.view(-1), N, T, 0, B)
-    W, rank = dist.get_world_size(), dist.get_rank()
-    gathered = torch.empty(W * B * N, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(gathered, valid.view(-1))
-    return NceInputs(posbits, gathered, N, T, rank * B, W * B)
+        valid_g, b_off, B_glob = valid.view(-1), 0, B
+    else:
+        W, rank = dist.get_world_size(), dist.get_rank()
+        valid_g = torch.empty(W * B * N, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(valid_g, valid.view(-1))
+        b_off, B_glob = rank * B, W * B
+    if not (compact and COMPACT_COLUMNS):
+        return NceInputs(posbits, valid_g, N, T, b_off, B_glob)
+    import numpy as np
+    n_loc = [min(len(s_), N) for s_ in start_list]
+    n_glob = n_loc if dist is None else _host_all_gather_int(n_loc, device)
+    off = np.zeros(B_glob + 1, np.int32)
+    np.cumsum(np.asarray(n_glob, np.int64), out=off[1:])
+    src = np.concatenate([b * N + np.arange(n, dtype=np.int64) for b, n in enumerate(n_glob)]) if off[-1] else \
+        np.zeros(0, np.int64)
+    pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
+    col_off = torch.from_numpy(off)
+    col_src = torch.from_numpy(src)
+    if pin:
+        col_off, col_src = col_off.pin_memory(), col_src.pin_memory()
+    col_off, col_src = col_off.to(device, non_blocking=True), col_src.to(device, non_blocking=True)
+    covered = torch.zeros(B_glob * N, dtype=torch.bool, device=device)
+    covered[col_src] = True
+    poison = (valid_g.bool() & ~covered).any()
+    return NceInputs(posbits, valid_g.index_select(0, col_src).contiguous(), N, T, b_off, B_glob, col_off=col_off,
+                     col_src=col_src, poison=poison)
 
 
 def nce_stats_to_loss(out4: torch.Tensor) -> torch.Tensor:
@@ -221,8 +313,9 @@ def nce_sums_one_model(logits, nce: NceInputs, shard: bool):
         dev = vfeat.device
         if dist is not None:
             tfeat = gather_text_features(tfeat, logits.shared_text, dist)
+        tfeat = nce.compact_features(tfeat)
         C = tfeat.shape[-2]
-        g = ops.sim_geom(B, S, T, C, nce.N, d, nce.b_off)
+        g = nce.geom(B, S, T, d)
         row_sums = torch.empty(2, B * S * T, dtype=torch.float32, device=dev)
         col_sums = torch.empty(2, S, C, dtype=torch.float32, device=dev)
         ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dev)
@@ -231,6 +324,8 @@ def nce_sums_one_model(logits, nce: NceInputs, shard: bool):
     else:
         if logits.dim() != 5:
             raise TanError(f"logits must be [B,S,T,B,N], got {tuple(logits.shape)}")
+        if nce.compact:
+            raise TanError("materialised logits keep the padded [B,S,T,B,N] layout: prepare the targets with compact=False")
         B, S, T, B2, N = logits.shape
         dev = logits.device
         if not logits.is_cuda:
@@ -254,7 +349,7 @@ def nce_loss_one_model(logits, nce: NceInputs, shard: bool) -> torch.Tensor:
     """loss_x for one model's logits."""
     dist = _dist() if shard else None
     row_sums, col_sums, T = nce_sums_one_model(logits, nce, shard)
-    return finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel, reduce_cols=False)
+    return nce.guard(finish_loss(row_sums, col_sums, dist, T, row_sel=nce.row_sel, col_sel=nce.col_sel, reduce_cols=False))
 
 
 def pack_text_features(td: torch.Tensor, tj: torch.Tensor) -> torch.Tensor:
@@ -300,13 +395,14 @@ def sim_pair_sums(vd, vj, full, nce: NceInputs):
     B, Sd, T, d = vd.shape
     Sj = vj.shape[1]
     dev = vd.device
+    full = nce.compact_features(full)
     C = full.shape[1]
     cols = torch.empty(2 * (Sd + Sj) * C, dtype=torch.float32, device=dev)
     cs_d, cs_j = cols[:2 * Sd * C].view(2, Sd, C), cols[2 * Sd * C:].view(2, Sj, C)
     rs_d = torch.empty(2, B * Sd * T, dtype=torch.float32, device=dev)
     rs_j = torch.empty(2, B * Sj * T, dtype=torch.float32, device=dev)
-    g_d = ops.sim_geom(B, Sd, T, C, nce.N, d, nce.b_off)
-    g_j = ops.sim_geom(B, Sj, T, C, nce.N, d, nce.b_off)
+    g_d = nce.geom(B, Sd, T, d)
+    g_j = nce.geom(B, Sj, T, d)
     ws = torch.empty(max(ops.sim_workspace_bytes(g_d), ops.sim_workspace_bytes(g_j)), dtype=torch.uint8, device=dev)
     ops.sim_nce_fwd(vd, full[0], 0, g_d, nce.posbits, nce.col_valid, None, rs_d, cs_d, ws, row_kill=nce.row_kill)
     ops.sim_nce_fwd(vj, full[1:], C * d, g_j, nce.posbits, nce.col_valid, None, rs_j, cs_j, ws, row_kill=nce.row_kill)
@@ -324,16 +420,16 @@ def nce_losses_pair(logits_dual, logits_joint, nce: NceInputs, shard: bool):
     vd, vj = logits_dual.vfeat, logits_joint.vfeat
     Sd, T, Sj = vd.shape[1], vd.shape[2], vj.shape[1]
     full = exchange_text_features(pack_text_features(logits_dual.tfeat, logits_joint.tfeat), dist)
-    C = full.shape[1]
     rs_d, cs_d, rs_j, cs_j, cols = sim_pair_sums(vd, vj, full, nce)
+    C = cs_d.shape[2]
     dist.all_reduce(cols)
     out8 = torch.zeros(8, dtype=torch.float64, device=vd.device)
     ops.nce_reduce(rs_d, cs_d, out8[0:4], Sd, T, C, nce.row_sel, nce.col_sel)
     ops.nce_reduce(rs_j, cs_j, out8[4:8], Sj, T, C, nce.row_sel, nce.col_sel)
     rows = torch.cat((out8[0:2], out8[4:6]))
     dist.all_reduce(rows)
-    loss_d = nce_stats_to_loss(torch.cat((rows[0:2], out8[2:4])))
-    loss_j = nce_stats_to_loss(torch.cat((rows[2:4], out8[6:8])))
+    loss_d = nce.guard(nce_stats_to_loss(torch.cat((rows[0:2], out8[2:4]))))
+    loss_j = nce.guard(nce_stats_to_loss(torch.cat((rows[2:4], out8[6:8]))))
     return loss_d, loss_j
 
 
@@ -432,7 +528,12 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
                            "temporalalignnet_b200.loss.pad_text_to_global(lang_embed, lang_padding_mask) before the "
                            "forward, and give every rank the same number of clips.")
     padded = (input_data['start_pad'], input_data['end_pad']) if 'start_pad' in input_data else None
-    nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard, padded=padded)
+    # ragged columns (padded sentences never computed): the plain recipe on fused logits; the flag branches index
+    # [B*N]-shaped vectors by padded column and the N > 64 gradient path has no ragged variant
+    compact = (not (learn or thr > 0 or head) and N <= 64 and isinstance(logits_dual, LazyLogits)
+               and isinstance(logits_joint, LazyLogits))
+    nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard, padded=padded,
+                             compact=compact)
     loss_dict = {}
     # training step: the forward ran with a tape (model.enable_autograd) -> the returned loss carries ONE autograd
     # node whose backward is the hand-written backward pass (train.py)
@@ -442,8 +543,8 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
         from . import train
         rs_d, cs_d, _ = nce_sums_one_model(logits_dual, nce, shard)
         rs_j, cs_j, _ = nce_sums_one_model(logits_joint, nce, shard)
-        loss_dual = finish_loss(rs_d, cs_d, dist, T, reduce_cols=False)
-        loss_joint = finish_loss(rs_j, cs_j, dist, T, reduce_cols=False)
+        loss_dual = nce.guard(finish_loss(rs_d, cs_d, dist, T, reduce_cols=False))
+        loss_joint = nce.guard(finish_loss(rs_j, cs_j, dist, T, reduce_cols=False))
         loss_dict['loss-dual'], loss_dict['loss-joint'] = loss_dual.detach(), loss_joint.detach()
         loss_dict['loss'] = train.attach_autograd((loss_dual + loss_joint) / 2, tape,
                                                   train.SimCtx(logits_dual, rs_d, cs_d, nce),

@@ -96,6 +96,25 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         M, N, K, act, _stream()), "tan_linear_bf16"))
 
 
+def linear_dual(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out_act: torch.Tensor,
+                out_pre: torch.Tensor, act: int = _lib.ACT_QUICKGELU) -> None:
+    """tan_linear_dual_bf16: out_act = act(a @ w.T + bias) and out_pre = a @ w.T + bias (both bf16) from one GEMM."""
+    M, K = a.shape
+    N = w.shape[0]
+    _launch("linear", 2.0 * M * N * K, 1, lambda: check(lib().tan_linear_dual_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _ptr(bias), out_act.data_ptr(), out_act.stride(0),
+        out_pre.data_ptr(), out_pre.stride(0), M, N, K, act, _stream()), "tan_linear_dual_bf16"))
+
+
+def linear_gelu_bwd(a: torch.Tensor, w: torch.Tensor, u: torch.Tensor, out: torch.Tensor) -> None:
+    """tan_linear_gelu_bwd_bf16: out = (a @ w.T) * gelu'(u)  (dgrad through c_proj and QuickGELU in one GEMM)."""
+    M, K = a.shape
+    N = w.shape[0]
+    _launch("dgrad", 2.0 * M * N * K, 1, lambda: check(lib().tan_linear_gelu_bwd_bf16(
+        a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), u.data_ptr(), u.stride(0), out.data_ptr(), out.stride(0),
+        M, N, K, _stream()), "tan_linear_gelu_bwd_bf16"))
+
+
 def linear_res_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
                   gamma: torch.Tensor, beta: torch.Tensor, out_bf16: torch.Tensor) -> None:
     """x += a @ w.T + bias (fp32, in place); out_bf16 = LayerNorm(x) * gamma + beta  (tan_linear_res_ln_bf16;
@@ -145,8 +164,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kpm_u8: Optiona
         out.stride(0), B, H, Lq, Lk, _ptr(lse), _stream()), "tan_attention_bf16"))
 
 
-def sim_geom(B_loc, S, T, C_, N, d, b_off=0) -> SimGeom:
-    return SimGeom(B_loc, S, T, C_, N, d, b_off)
+def sim_geom(B_loc, S, T, C_, N, d, b_off=0, col_off: Optional[torch.Tensor] = None) -> SimGeom:
+    """struct tan_sim_geom; col_off (device int32 [B_glob + 1]) switches to ragged columns (see include/tan_b200.h).
+    The returned struct only holds the POINTER: the caller keeps `col_off` alive."""
+    return SimGeom(B_loc, S, T, C_, N, d, b_off, _ptr(col_off))
 
 
 def sim_workspace_bytes(g: SimGeom) -> int:

@@ -87,7 +87,7 @@ class TanStepRunner:
         self.d_tpm = self.h_tpm.to(self.device)
         self.input_data = {"start": self.batch["start"], "end": self.batch["end"], "text": self.batch["text_str"]}
         self.nce = loss_mod.prepare_nce_inputs(self.batch["start"], self.batch["end"], self.d_tpm, T, self.N,
-                                               self.device, self.shard)
+                                               self.device, self.shard, compact=not self.flags and self.N <= 64)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_video, self.h_text, self.h_vpm, self.h_tpm))
         self.d2h_bytes = 4
         self._graph: Optional[torch.cuda.CUDAGraph] = None

@@ -34,6 +34,10 @@ AUTOGRAD_DEFAULT = os.environ.get("TAN_AUTOGRAD", "0") != "0"
 SIM_BWD_ROWS = int(os.environ.get("TAN_SIM_BWD_ROWS", "65536"))
 SIM_BWD_G_BYTES = 2 << 30
 SIM_GRAD_FUSED = os.environ.get("TAN_SIM_GRAD_FUSED", "1") != "0"     # G in the epilogue of the recomputation GEMM
+# QuickGELU inside the GEMM epilogues of the training step: c_fc writes pre-activation AND activation
+# (tan_linear_dual_bf16), the dgrad through c_proj multiplies with gelu'(u) (tan_linear_gelu_bwd_bf16) -- instead of
+# two elementwise passes over the [M, 4d] activations per layer
+FUSE_GELU = os.environ.get("TAN_FUSE_GELU", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -131,9 +135,12 @@ def run_encoder_stack_train(enc, x0: torch.Tensor, kpm, B: int, L: int, l_split:
         lt.xn2 = torch.empty(M, d, **bf)
         ops.layernorm(lt.x1, M, d, gamma=_f32(blk.ln_2.weight), beta=_f32(blk.ln_2.bias), L_in=L, out_bf16=lt.xn2)
         lt.u = torch.empty(M, 4 * d, **bf)
-        ops.linear(lt.xn2, cache.get(blk.mlp.c_fc.weight), _f32(blk.mlp.c_fc.bias), out_bf16=lt.u, act=ACT_NONE)
         lt.h = torch.empty(M, 4 * d, **bf)
-        ops.quickgelu_fwd(lt.u, lt.h)
+        if FUSE_GELU:
+            ops.linear_dual(lt.xn2, cache.get(blk.mlp.c_fc.weight), _f32(blk.mlp.c_fc.bias), out_act=lt.h, out_pre=lt.u)
+        else:
+            ops.linear(lt.xn2, cache.get(blk.mlp.c_fc.weight), _f32(blk.mlp.c_fc.bias), out_bf16=lt.u, act=ACT_NONE)
+            ops.quickgelu_fwd(lt.u, lt.h)
         x_next = torch.empty(M, d, **f32)
         ops.linear(lt.h, cache.get(blk.mlp.c_proj.weight), _f32(blk.mlp.c_proj.bias), residual=lt.x1, out_f32=x_next)
         x = x_next
@@ -296,9 +303,13 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
         H = blk.n_head
         # ---- MLP: x_out = x1 + c_proj(gelu(c_fc(ln_2(x1)))) ------------------------------------------
         ops.cast_bf16(dx, dxb)
-        _dgrad(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), out_bf16=dh)
-        _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
-        ops.quickgelu_bwd(dh, lt.u, dh)                                        # du, in place
+        if FUSE_GELU:        # du = (dx @ W_proj) o gelu'(u) in one GEMM
+            ops.linear_gelu_bwd(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), lt.u, dh)
+            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
+        else:
+            _dgrad(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), out_bf16=dh)
+            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
+            ops.quickgelu_bwd(dh, lt.u, dh)                                    # du, in place
         _dgrad(dh, ops.transpose_bf16(cache.get(blk.mlp.c_fc.weight)), out_f32=dy32)
         _wgrad(dh, lt.xn2, grads.of(blk.mlp.c_fc.weight), grads.of(blk.mlp.c_fc.bias))
         ops.layernorm_bwd(dy32, lt.x1, _f32(blk.ln_2.weight), dx, True, M, d, grads.of(blk.ln_2.weight),
@@ -369,6 +380,7 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
     dev = vfeat.device
     if dist is not None:
         tfeat = gather_text_features(tfeat, lg.shared_text, dist)
+    tfeat = nce.compact_features(tfeat)            # ragged columns: the padded sentences are not computed at all
     S_t = 1 if lg.shared_text else S
     tfeat = tfeat.view(S_t, -1, d)
     C = tfeat.shape[1]
@@ -382,7 +394,7 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
     vsm = vfeat.permute(1, 0, 2, 3).reshape(S, B * T, d).contiguous()         # stage-major rows
     R = B * T
     Rc = min(R, SIM_BWD_ROWS, max(256, (SIM_BWD_G_BYTES // (2 * Cp)) // 256 * 256))
-    g = ops.sim_geom(B, 1, T, C, nce.N, d, nce.b_off)
+    g = nce.geom(B, 1, T, d)
     fused = SIM_GRAD_FUSED and nce.N <= 64 and d % 64 == 0
     z = None if fused else torch.empty(Rc, Cp, dtype=torch.float32, device=dev)
     G = torch.empty(Rc, Cp, dtype=torch.bfloat16, device=dev)
@@ -407,7 +419,7 @@ def sim_backward(ctx: SimCtx, scale: torch.Tensor, dist):
             ops.linear(G[:rc], tT, out_f32=d_v[s, r0:r0 + rc], tag="sim_bwd")                # dA = G @ text
             # dB += G^T @ video straight from G and the video rows as they lie (MN-major operands): no transposes
             ops.gemm_tn(G[:rc], a, d_t[si], accumulate=True, tag="sim_bwd")
-    return d_v, d_t
+    return d_v, nce.scatter_columns(d_t)       # text gradients back in the padded [B_glob * N] column layout
 
 
 def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out: torch.Tensor, nce_weight: float,

@@ -138,6 +138,29 @@ def transpose_bf16(x, out=None):
     return out
 
 
+def linear_dual(a, w, bias, out_act, out_pre, act=1):
+    y = a.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    out_pre.copy_(y.to(BF))
+    out_act.copy_((y * torch.sigmoid(1.702 * y) if act == 1 else y).to(BF))
+
+
+def linear_gelu_bwd(a, w, u, out):
+    y = a.float() @ w.float().t()
+    x = u.float()
+    s = torch.sigmoid(1.702 * x)
+    out.copy_((y * s * (1 + 1.702 * x * (1 - s))).to(BF))
+
+
+def embed_gather(ids, table, out=None):
+    r = table[ids.long()]
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
 def ema_update(target_params, online_params, m):
     """Stand-in of optim.ema_update (tan_ema_update): in place on the Parameters, so version counters advance."""
     with torch.no_grad():
@@ -190,13 +213,23 @@ def batch_sum(x, out, B, L, d, L_out, l_off, accumulate):
     out.copy_(out + s if accumulate else s)
 
 
+def _own_cols(g, b):
+    """Columns [c0, c1) of local clip b (ragged layout when g.col_off points at a HOST int32 prefix array)."""
+    if g.col_off:
+        import ctypes
+        arr = (ctypes.c_int32 * (g.b_off + b + 2)).from_address(g.col_off)
+        return int(arr[g.b_off + b]), int(arr[g.b_off + b + 1])
+    return (g.b_off + b) * g.N, (g.b_off + b + 1) * g.N
+
+
 def _pos_matrix(g, posbits, Rc, r0):
     """[Rc, C] positives of rows r0.. of one stage (row = b * T + t, local clips)."""
     pos_bnt = unpack_posbits(posbits, g.N)                               # [B, N, T]
     pos = torch.zeros(Rc, g.C)
     for i in range(Rc):
         b, t = divmod(r0 + i, g.T)
-        pos[i, (g.b_off + b) * g.N:(g.b_off + b + 1) * g.N] = pos_bnt[b, :, t].float()
+        c0, c1 = _own_cols(g, b)
+        pos[i, c0:c1] = pos_bnt[b, :c1 - c0, t].float()
     return pos
 
 
@@ -207,7 +240,8 @@ def _grad_matrix(cos, Rc, r0, g, posbits, col_valid, row_kill, ra, rap, cb, cbp)
         own = torch.zeros(Rc, g.C)
         for i in range(Rc):
             b = (r0 + i) // g.T
-            own[i, (g.b_off + b) * g.N:(g.b_off + b + 1) * g.N] = 1.0
+            c0, c1 = _own_cols(g, b)
+            own[i, c0:c1] = 1.0
         e = e * (1.0 - own * row_kill.reshape(-1)[r0:r0 + Rc].float()[:, None])
     rr = slice(r0, r0 + Rc)
     return e * (ra[rr][:, None] + cb[None, :g.C] - pos * (rap[rr][:, None] + cbp[None, :g.C])) / 0.07
@@ -251,7 +285,8 @@ def sim_nce_fwd(vfeat, tfeat, tfeat_stage_stride, g, posbits, col_valid, logits_
     if row_kill is not None:
         own = torch.zeros(B, 1, 1, C)
         for b in range(B):
-            own[b, 0, 0, (g.b_off + b) * N:(g.b_off + b + 1) * N] = 1.0
+            c0, c1 = _own_cols(g, b)
+            own[b, 0, 0, c0:c1] = 1.0
         e = e * (1.0 - own * row_kill.view(B, 1, T, 1).float())
     pe = e * pos
     row_sums.copy_(torch.stack((e.sum(-1).reshape(-1), pe.sum(-1).reshape(-1))))
@@ -296,7 +331,7 @@ def agree_scan(own, posbits, vpm_u8, tpm_u8, B, T, N, fill_max):
     return win, torch.zeros(B, N), z.max(dim=1).values
 
 
-NAMES = ["gemm_tn", "own_clip_sim", "agree_scan", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
+NAMES = ["gemm_tn", "linear_dual", "linear_gelu_bwd", "embed_gather", "own_clip_sim", "agree_scan", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
          "transpose_bf16", "colsum", "layernorm_bwd", "l2norm_bwd", "batch_sum", "sim_grad_gemm", "sim_grad_tiles",
          "pos_from_time", "sim_workspace_bytes", "sim_nce_fwd", "nce_reduce"]
 

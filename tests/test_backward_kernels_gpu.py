@@ -332,3 +332,28 @@ def test_gemm_tn_pitched_operands():
     ops.gemm_tn(a, b, out, accumulate=False)
     ref = a.float().t() @ b.float()
     assert (out - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 2048, 512), (4096, 2048, 512), (1000, 512, 128)])
+def test_linear_dual_and_gelu_bwd_epilogues(M, N, K):
+    """tan_linear_dual_bf16 (pre-activation + QuickGELU from one GEMM) and tan_linear_gelu_bwd_bf16
+    ((A W^T) o gelu'(u)) against torch on the same bf16 inputs."""
+    ops = _ops()
+    a = _rand(M, K, seed=51).to(torch.bfloat16)
+    w = (_rand(N, K, seed=52) * 0.05).to(torch.bfloat16)
+    b = _rand(N, seed=53) * 0.1
+    act = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    pre = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.linear_dual(a, w, b, act, pre)
+    y = a.float() @ w.float().t() + b
+    assert ((pre.float() - y).norm() / y.norm()).item() < 4e-3
+    h = y * torch.sigmoid(1.702 * y)
+    assert ((act.float() - h).norm() / h.norm()).item() < 5e-3
+    # backward: dh = g @ w2^T, du = dh * gelu'(u)
+    g = _rand(M, K, seed=54).to(torch.bfloat16)
+    du = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_gelu_bwd(g, w, pre, du)
+    x = pre.float()
+    s = torch.sigmoid(1.702 * x)
+    ref = (g.float() @ w.float().t()) * s * (1 + 1.702 * x * (1 - s))
+    assert ((du.float() - ref).norm() / ref.norm()).item() < 6e-3

@@ -46,7 +46,7 @@ def test_abi_version_and_error_string(lib):
 
 def test_struct_layouts_match_header():
     from temporalalignnet_b200._lib import LnArgs, SimGeom
-    assert ctypes.sizeof(SimGeom) == 7 * 4
+    assert ctypes.sizeof(SimGeom) == 40 and SimGeom.col_off.offset == 32
     # 64-bit: pointers 8-byte aligned; the header's field order packs to this size
     assert ctypes.sizeof(LnArgs) == 152 and LnArgs.out_f32.offset == 64 and LnArgs.strideA.offset == 88
 

@@ -47,3 +47,32 @@ def test_nce_stats_to_loss_and_circulant():
     out4 = torch.tensor([6.0, 3.0, 8.0, 2.0], dtype=torch.float64)
     assert float(L.nce_stats_to_loss(out4)) == pytest.approx((6 / 3 + 8 / 2) / 2)
     assert L.circulant(torch.tensor([0, 1, 2]), dim=0).tolist() == [[0, 1, 2], [2, 0, 1], [1, 2, 0]]
+
+
+def test_compact_column_layout_and_poison_flag():
+    """Ragged columns (NceInputs.col_off / col_src): clip b owns columns [off[b], off[b+1]) in sentence order; a padding
+    mask that marks a sentence beyond the list length as real poisons the loss instead of silently dropping it."""
+    import torch
+    from temporalalignnet_b200 import loss as L, synth
+    from tests.helpers import cpu_pos_from_time
+    b = synth.make_batch(4, 16, 6, seed=21)
+    tpm = torch.from_numpy(b["text_padding_mask"])
+    nce = L.prepare_nce_inputs(b["start"], b["end"], tpm, 16, 6, torch.device("cpu"), shard=False,
+                               pos_fn=cpu_pos_from_time, compact=True)
+    n = [len(s) for s in b["start"]]
+    assert nce.compact and nce.C == sum(n) and nce.C_pad == 24
+    assert nce.col_off.tolist() == [0] + list(torch.tensor(n).cumsum(0).tolist())
+    assert nce.col_src.tolist() == [i * 6 + j for i, k in enumerate(n) for j in range(k)]
+    assert bool(nce.col_valid.all()) and not bool(nce.poison)
+    x = torch.arange(2 * nce.C * 3, dtype=torch.float32).view(2, nce.C, 3)
+    full = nce.scatter_columns(x)
+    assert tuple(full.shape) == (2, 24, 3) and torch.equal(full[:, nce.col_src], x)
+    assert float(full.sum()) == float(x.sum())
+    assert float(L.NceInputs.guard(nce, torch.tensor(1.5))) == 1.5
+    tpm2 = tpm.clone()
+    short = min(range(4), key=lambda i: n[i])
+    if n[short] < 6:
+        tpm2[short, n[short]] = False                      # a "real" sentence the lists know nothing about
+        nce2 = L.prepare_nce_inputs(b["start"], b["end"], tpm2, 16, 6, torch.device("cpu"), shard=False,
+                                    pos_fn=cpu_pos_from_time, compact=True)
+        assert bool(nce2.poison) and torch.isnan(nce2.guard(torch.tensor(1.5)))
