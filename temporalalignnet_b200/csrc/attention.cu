@@ -46,6 +46,14 @@ static_assert(2 * (kAttSmem + 1024) <= 228 * 1024, "two CTAs per SM");
 
 __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// Development aid (tan_debug_set_trace): per-CTA clock64 stamps, 128 slots per CTA for the first 512 CTAs.
+// 0 globaltimer, 1 start, 2 prologue done, 3 exit; block g < 10 at 8 + 10 g: +0 K issued, +1 V issued (producer),
+// +2 QK issued, +3 p_ready seen, +4 PV issued (MMA warp), +5 s_full seen, +6 S in registers, +7 P staged (softmax warp 2)
+extern __device__ long long* g_gemm_trace;
+__device__ __forceinline__ void att_trace(long long* tr, int g, int k) {
+  if (tr != nullptr && g < 10) tr[8 + 10 * g + k] = clock64();
+}
+
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const uint8_t* __restrict__ kpm, bf16* __restrict__ out,
@@ -74,6 +82,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* tr = g_gemm_trace;
+  {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    tr = (tr != nullptr && cta < 512) ? tr + cta * 128 : nullptr;
+    if (tr != nullptr && threadIdx.x == 0) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      tr[0] = gt;
+      tr[1] = clock64();
+    }
+  }
   // this CTA's query tiles: [qt0, qt0 + nq) (all of them unless the launch splits long sequences over blockIdx.z)
   const int qt0 = blockIdx.z * tiles_per_cta;
   const int nq = min(tiles_per_cta, (Lq + kAttBQ - 1) / kAttBQ - qt0);
@@ -103,6 +122,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();
+  if (tr != nullptr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -118,9 +138,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_wait_relaxed(&k_empty[ks], ((g / kAttKStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&k_full[ks], kAttKVBytes);
           tma_load_2d(sK + ks * kAttKVBytes, &tmK, &k_full[ks], h * 64, b * Lk + j * kAttBK);
+          att_trace(tr, g, 0);
           mbar_wait_relaxed(&v_empty[vs], ((g / kAttVStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&v_full[vs], kAttKVBytes);
           tma_load_2d(sV + vs * kAttKVBytes, &tmV, &v_full[vs], h * 64, b * Lk + j * kAttBK);
+          att_trace(tr, g, 1);
         }
       }
     }
@@ -142,6 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * kAttKVBytes));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + (g & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        att_trace(tr, g, 2);
         tc_commit(&s_full[g & 1]);
         tc_commit(&k_empty[ks]);
         if (j == nb - 1) tc_commit(&q_empty[qb]);
@@ -154,6 +177,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int qt = g / nb, j = g - qt * nb;
       const int ob = qt & 1, vs = g % kAttVStages;
       mbar_wait(&p_ready[g & 1], (g >> 1) & 1);  // P_g is in shared memory, S_g consumed, O rescaled if needed
+      if (lane == 0) att_trace(tr, g, 3);
       if (j == 0 && qt >= 2) mbar_wait(&o_free[ob], ((qt >> 1) - 1) & 1);   // tile qt-2 has left this O buffer
       mbar_wait(&v_full[vs], (g / kAttVStages) & 1);
       tc_fence_after();
@@ -164,6 +188,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16_ss(tmem_base + 128 + ob * 64, dp + 2 * k, dv + 128 * k, idesc_pv, (j | k) != 0);
+        att_trace(tr, g, 4);
         tc_commit(&pv_done[g & 1]);
         tc_commit(&v_empty[vs]);
       }
@@ -200,6 +225,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int g = qt * nb + j;
         mbar_wait(&s_full[g & 1], (g >> 1) & 1);
         tc_fence_after();
+        long long* trw = (warp == 2 && lane == 0) ? tr : nullptr;
+        att_trace(trw, g, 5);
         if (live) {
           // key mask of this block as two warp-uniform words (bit set = ignore key)
           uint32_t w0, w1;
@@ -218,6 +245,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_ld_32x32(t_s, r0);
           tmem_ld_32x32(t_s + 32, r1);
           tmem_ld_wait();
+          att_trace(trw, g, 6);
           float mx = -INFINITY;
           if ((w0 | w1) != 0u) {
 #pragma unroll
@@ -275,6 +303,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             *reinterpret_cast<uint4*>(sPg + att_swz(row, ch)) =
                 make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
           fence_proxy_async_smem();                  // P visible to the tensor core (async proxy)
+          att_trace(trw, g, 7);
         }
         tc_fence_before();                           // S reads / O writes retired before the MMAs that follow p_ready
         __syncwarp();
@@ -335,6 +364,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (tr != nullptr && threadIdx.x == 0) tr[3] = clock64();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
