@@ -32,6 +32,17 @@ constexpr int kAttBK = 64;
 constexpr int kAttThreads = 192;
 constexpr int kAttQBytes = kAttBQ * 128;      // 16 KB
 constexpr int kAttKVBytes = kAttBK * 128;     // 8 KB
+// Round-2 per-CTA timelines (scripts/attn_trace.py; profiles/r02i_attention_timeline_before.txt): at L = 256 a CTA lives ~26 k
+// clk = 5.4 k until its first QK (prologue + ~3.7 k clk for the first Q / K boxes), 8 blocks at a ~2.0 k clk cadence
+// and two tile epilogues of ~3.3 k clk (half of it waiting for the tile's last PV).  The softmax of a block takes
+// ~1.35 k clk; the rest of the cadence is the MMA warp's serial path between p_ready(g) and a usable S_{g+2}: ~0.2 k
+// to see the barrier, 4 tcgen05.mma ~0.23 k (~55 clk per issue), two tcgen05.commit + the next waits ~0.65 k, 4 more
+// MMAs.  Three variants were measured against that picture and REJECTED (same box, kept under profiles/):
+//   * L2 prefetch of every K / V / Q box at CTA start (r02j): the prefetches queue ahead of the real loads (first QK
+//     at 9.6 k instead of 5.1 k clk), the cadence does not change -- the loads are not what paces the blocks;
+//   * 4-deep K and V rings with a single P buffer (r02k): 178.9 vs 182.7 us per launch, within noise;
+//   * releasing S_g as soon as it is in registers and issuing QK_{g+2} during the softmax of block g (r02l): PV_g
+//     then waits behind issue_qk's K wait, softmax blocks lengthen to ~1.5 k clk, 188 vs 169 us per launch.
 // Ring depths (a 3-deep K ring was measured slower: 1.96 vs 1.62 ms per step at the bench shape).  The dynamic
 // segment is declared 1024-byte aligned instead of carrying an alignment slack; two CTAs per SM.
 #ifndef TAN_ATT_KSTAGES
