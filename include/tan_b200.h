@@ -320,11 +320,13 @@ TAN_API int tan_quickgelu_bwd(const void* dh, const void* u, void* du, size_t n,
  * (r / L_in) * L_out + l_off + r % L_in of dy):  dx[r] (+)= the LayerNorm input gradient (accumulate_dx != 0 adds
  * to dx: the residual stream's gradient), dgamma / dbeta [d] are ACCUMULATED (NULL: skipped).  x, dx [rows, d]
  * fp32, dy fp32.  Replaces autograd of nn.LayerNorm at model/tfm_model.py:31,:37, model/tan_model.py:155,:161-167,
- * :174,:187,:206,:233. */
+ * :174,:187,:206,:233.  * dx_bf16 (optional, [rows, d] bf16): a bf16 copy of the UPDATED dx; dx_colsum (optional, [d] fp32, accumulated;
+ * needs dgamma / dbeta): its column sums -- the operand and the bias gradient of the linear layer whose backward comes
+ * next, produced here instead of by a cast pass and a column-sum pass over the residual-stream gradient. */
 TAN_API size_t tan_layernorm_bwd_workspace_bytes(int rows, int d);
 TAN_API int tan_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate_dx,
                               int rows, int d, int L_in, int L_out, int l_off, float* dgamma, float* dbeta,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              void* dx_bf16, float* dx_colsum, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of y = x / ||x|| (model/tan_model.py:116-117,:136-137): dst = (g - y <y, g>) / ||x||.  Row r of the raw
  * features x lies at (r / L_in) * src_stride + r % L_in, of the incoming gradient g at (r / L_in) * g_stride +

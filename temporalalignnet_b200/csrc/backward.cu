@@ -139,27 +139,17 @@ __global__ void __launch_bounds__(256) quickgelu_bwd_kernel(const uint4* __restr
 // Warp per row, the row lives in registers (statistics are recomputed from x, as in the forward kernel).
 // ------------------------------------------------------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             int accumulate, int rows, int d, int L_in, int L_out,
-                                                            int l_off, float* __restrict__ partial) {
+                                                            int l_off, float* __restrict__ partial,
+                                                            bf16* __restrict__ dx_bf16, int want_colsum) {
   __shared__ float red[8][V * 128];
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dg[V * 4], db[V * 4];
+  float dg[V * 4], db[V * 4], dsum[V * 4];     // dsum: column sums of the UPDATED dx (the next linear's bias gradient)
 #pragma unroll
-  for (int i = 0; i < V * 4; ++i) { dg[i] = 0.f; db[i] = 0.f; }
-  float gm[V * 4];
-  if (gamma != nullptr) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-      gm[4 * i] = g.x; gm[4 * i + 1] = g.y; gm[4 * i + 2] = g.z; gm[4 * i + 3] = g.w;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < V * 4; ++i) gm[i] = 1.f;
-  }
+  for (int i = 0; i < V * 4; ++i) { dg[i] = 0.f; db[i] = 0.f; dsum[i] = 0.f; }
   for (int r = blockIdx.x * warps_per_block + warp; r < rows; r += gridDim.x * warps_per_block) {
     const int b = r / L_in, l = r - b * L_in;
     const int64_t yr = static_cast<int64_t>(b) * L_out + l_off + l;
@@ -180,13 +170,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 #pragma unroll
     for (int i = 0; i < V * 4; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
     const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    // gamma is re-read per row (L1-resident): holding it would cost 4 V registers and, with the column-sum
+    // accumulators, push the kernel from 2 CTAs per SM to 1 (measured: 3.5 -> 7.7 ms per step)
+    float gmv[V * 4];
+    if (gamma != nullptr) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        gmv[4 * i] = g4.x; gmv[4 * i + 1] = g4.y; gmv[4 * i + 2] = g4.z; gmv[4 * i + 3] = g4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V * 4; ++i) gmv[i] = 1.f;
+    }
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int i = 0; i < V * 4; ++i) {
       xv[i] *= rstd;                       // xhat
       dg[i] += gv[i] * xv[i];
       db[i] += gv[i];
-      gv[i] *= gm[i];                      // g
+      gv[i] *= gmv[i];                     // g
       sg += gv[i];
       sgx += gv[i] * xv[i];
     }
@@ -204,22 +207,27 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
       pd[i * 32 + lane] = o;
+      if (dx_bf16 != nullptr)      // the bf16 copy the following dgrad / wgrad GEMMs read (was a separate cast pass)
+        *reinterpret_cast<uint2*>(dx_bf16 + static_cast<int64_t>(r) * d + 4 * (i * 32 + lane)) =
+            make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      dsum[4 * i] += o.x; dsum[4 * i + 1] += o.y; dsum[4 * i + 2] += o.z; dsum[4 * i + 3] += o.w;
     }
   }
   if (partial == nullptr) return;
   // block reduction of dgamma then dbeta over the 8 warps (column j of lane: 128 i + 4 lane + k)
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  const int passes = want_colsum ? 3 : 2;
+  for (int pass = 0; pass < passes; ++pass) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) red[warp][i * 128 + 4 * lane + k] = pass == 0 ? dg[4 * i + k] : db[4 * i + k];
+      for (int k = 0; k < 4; ++k)
+        red[warp][i * 128 + 4 * lane + k] = pass == 0 ? dg[4 * i + k] : (pass == 1 ? db[4 * i + k] : dsum[4 * i + k]);
     __syncthreads();
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
       float t = 0.f;
       for (int w = 0; w < warps_per_block; ++w) t += red[w][j];
-      partial[(static_cast<int64_t>(blockIdx.x) * 2 + pass) * d + j] = t;
+      partial[(static_cast<int64_t>(blockIdx.x) * 3 + pass) * d + j] = t;
     }
   }
 }
@@ -227,16 +235,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // dgamma[j] += sum_p partial[p][0][j], dbeta[j] += sum_p partial[p][1][j]  (accumulated: one LayerNorm may serve
 // several calls of a step, e.g. ln_video_init in the video and the joint stack)
 __global__ void ln_param_finish_kernel(const float* __restrict__ partial, int blocks, int d, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
+                                       float* __restrict__ dbeta, float* __restrict__ dx_colsum) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= d) return;
-  float g = 0.f, b = 0.f;
+  float g = 0.f, b = 0.f, c = 0.f;
   for (int p = 0; p < blocks; ++p) {
-    g += partial[(static_cast<int64_t>(p) * 2) * d + j];
-    b += partial[(static_cast<int64_t>(p) * 2 + 1) * d + j];
+    g += partial[(static_cast<int64_t>(p) * 3) * d + j];
+    b += partial[(static_cast<int64_t>(p) * 3 + 1) * d + j];
+    if (dx_colsum != nullptr) c += partial[(static_cast<int64_t>(p) * 3 + 2) * d + j];
   }
   dgamma[j] += g;
   dbeta[j] += b;
+  if (dx_colsum != nullptr) dx_colsum[j] += c;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,12 +488,12 @@ static int ln_bwd_blocks(int rows) {
 }
 
 extern "C" size_t tan_layernorm_bwd_workspace_bytes(int rows, int d) {
-  return static_cast<size_t>(ln_bwd_blocks(rows)) * 2 * static_cast<size_t>(d) * sizeof(float);
+  return static_cast<size_t>(ln_bwd_blocks(rows)) * 3 * static_cast<size_t>(d) * sizeof(float);
 }
 
 extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx, int accumulate_dx,
                                  int rows, int d, int L_in, int L_out, int l_off, float* dgamma, float* dbeta,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
+                                 void* dx_bf16, float* dx_colsum, void* workspace, size_t workspace_bytes, void* stream) {
   TAN_CHECK(tan_device_check());
   if (dy == nullptr || x == nullptr || dx == nullptr) return set_error(TAN_ERR_ARG, "tan_layernorm_bwd: null pointer");
   if (rows <= 0) return TAN_OK;
@@ -492,6 +502,10 @@ extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* g
   if (L_in <= 0 || L_out < L_in + l_off || l_off < 0)
     return set_error(TAN_ERR_SHAPE, "tan_layernorm_bwd: bad row map (L_in=%d L_out=%d l_off=%d)", L_in, L_out, l_off);
   if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(TAN_ERR_ARG, "tan_layernorm_bwd: dgamma/dbeta mismatch");
+  if (dx_colsum != nullptr && dgamma == nullptr)
+    return set_error(TAN_ERR_ARG, "tan_layernorm_bwd: dx_colsum needs the parameter-gradient pass (dgamma / dbeta)");
+  if (dx_bf16 != nullptr && (reinterpret_cast<uintptr_t>(dx_bf16) & 7))
+    return set_error(TAN_ERR_SHAPE, "tan_layernorm_bwd: dx_bf16 must be 8-byte aligned");
   const int blocks = ln_bwd_blocks(rows);
   float* partial = nullptr;
   if (dgamma != nullptr) {
@@ -502,7 +516,7 @@ extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* g
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define TAN_LNB(V)                                                                                              \
   layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gamma, dx, accumulate_dx, rows, d, L_in, L_out, l_off, \
-                                                  partial)
+                                                  partial, static_cast<bf16*>(dx_bf16), dx_colsum != nullptr ? 1 : 0)
   switch (d / 128) {
     case 1: TAN_LNB(1); break;
     case 2: TAN_LNB(2); break;
@@ -516,7 +530,7 @@ extern "C" int tan_layernorm_bwd(const float* dy, const float* x, const float* g
 #undef TAN_LNB
   TAN_CUDA(cudaGetLastError());
   if (dgamma != nullptr) {
-    ln_param_finish_kernel<<<(d + 255) / 256, 256, 0, st>>>(partial, blocks, d, dgamma, dbeta);
+    ln_param_finish_kernel<<<(d + 255) / 256, 256, 0, st>>>(partial, blocks, d, dgamma, dbeta, dx_colsum);
     TAN_CUDA(cudaGetLastError());
   }
   return TAN_OK;

@@ -311,15 +311,18 @@ def quickgelu_bwd(dh: torch.Tensor, u: torch.Tensor, du: torch.Tensor) -> None:
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, dx: torch.Tensor, accumulate_dx: bool,
                   rows: int, d: int, dgamma: Optional[torch.Tensor], dbeta: Optional[torch.Tensor],
-                  L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0) -> None:
-    """tan_layernorm_bwd (dy, x, dx fp32; dgamma / dbeta accumulated)."""
+                  L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0,
+                  dx_bf16: Optional[torch.Tensor] = None, dx_colsum: Optional[torch.Tensor] = None) -> None:
+    """tan_layernorm_bwd (dy, x, dx fp32; dgamma / dbeta accumulated).  dx_bf16 / dx_colsum: bf16 copy and column
+    sums (accumulated) of the updated dx -- the operand and the bias gradient of the next linear's backward."""
     L_in = rows if L_in is None else L_in
     L_out = L_in if L_out is None else L_out
     nbytes = int(lib().tan_layernorm_bwd_workspace_bytes(rows, d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     _launch("ln_bwd", float(rows) * d, 2, lambda: check(lib().tan_layernorm_bwd(
         dy.data_ptr(), x.data_ptr(), _ptr(gamma), dx.data_ptr(), int(bool(accumulate_dx)), rows, d, L_in, L_out, l_off,
-        _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), nbytes, _stream()), "tan_layernorm_bwd"))
+        _ptr(dgamma), _ptr(dbeta), _ptr(dx_bf16), _ptr(dx_colsum), ws.data_ptr(), nbytes, _stream()),
+        "tan_layernorm_bwd"))
 
 
 def l2norm_bwd(x: torch.Tensor, g: torch.Tensor, dst: torch.Tensor, accumulate: bool, rows: int, d: int, L_in: int,

@@ -541,10 +541,9 @@ class TemporalAligner(nn.Module):
 
     def _eval_sim(self, vfeat, tfeat, shared_text, B, S, T, N):
         """Per-video similarity [B, S, T, N] = the diagonal blocks of the [B,S,T,B,N] matrix
-        (einsum 'bstc,b(s)kc->bstk', model/tan_model.py:261-262,:280-281)."""
-        dense = LazyLogits(vfeat, tfeat, shared_text, N).materialize()        # [B,S,T,B,N] bf16
-        idx = torch.arange(B, device=dense.device)
-        return dense[idx, :, :, idx, :].float()
+        (einsum 'bstc,b(s)kc->bstk', model/tan_model.py:261-262,:280-281): tan_own_clip_sim computes only those
+        blocks (fp32), instead of materialising all B^2 and indexing the diagonal."""
+        return ops.own_clip_sim(vfeat, tfeat, shared_text, B, S, T, N, self.width)
 
     @torch.no_grad()
     def get_text_visual_sim_joint(self, video_embed, lang_embed, interpolate_from=None):

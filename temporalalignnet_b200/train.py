@@ -247,10 +247,17 @@ def forward_train(model, video_embed, lang_embed, video_padding_mask=None, lang_
 # backward
 # ------------------------------------------------------------------------------------------------------
 class _Grads:
-    """fp32 gradient buffers per parameter (zero-initialised on first touch; kernels accumulate into them)."""
+    """fp32 gradient buffers per parameter (zero-initialised; kernels accumulate into them).  The parameters of one
+    transformer block live in ONE flat buffer (`bucket`), so that with several GPUs a finished block's gradients are
+    all-reduced by a single asynchronous collective that overlaps the backward pass of the blocks below it
+    ("bucketing per layer")."""
 
-    def __init__(self):
+    def __init__(self, dist=None):
         self.g = {}
+        self.dist = dist
+        self.buckets = {}          # id(block) -> flat tensor
+        self.pending = []          # async all-reduce handles
+        self.reduced = set()       # ids of parameters whose gradient is already summed over the ranks
 
     def of(self, p: torch.Tensor) -> torch.Tensor:
         t = self.g.get(id(p))
@@ -261,6 +268,34 @@ class _Grads:
 
     def get(self, p):
         return self.g.get(id(p))
+
+    def bucket(self, block) -> None:
+        """Place the gradient buffers of every trainable parameter of `block` in one flat tensor (before first use)."""
+        if id(block) in self.buckets:
+            return
+        ps = [p for p in block.parameters() if p.requires_grad and id(p) not in self.g]
+        if not ps:
+            return
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+        off = 0
+        for p in ps:
+            self.g[id(p)] = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.buckets[id(block)] = (flat, ps)
+
+    def reduce_bucket(self, block) -> None:
+        """All ranks have finished this block's gradients: sum them over the ranks, asynchronously."""
+        ent = self.buckets.get(id(block))
+        if self.dist is None or ent is None:
+            return
+        flat, ps = ent
+        self.pending.append(self.dist.all_reduce(flat, async_op=True))
+        self.reduced.update(id(p) for p in ps)
+
+    def wait(self) -> None:
+        for w in self.pending:
+            w.wait()
+        self.pending = []
 
 
 def _wgrad(dy_bf16: torch.Tensor, x_bf16: torch.Tensor, gw: torch.Tensor, gb: Optional[torch.Tensor] = None) -> None:
@@ -289,10 +324,15 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
     f32 = dict(dtype=torch.float32, device=dev)
     bf = dict(dtype=torch.bfloat16, device=dev)
     dx = torch.empty(M, d, **f32)
-    post = tape.post_ln
-    ops.layernorm_bwd(stage_grads[S - 1], tape.x_out, _f32(post.weight), dx, False, M, d, grads.of(post.weight),
-                      grads.of(post.bias))
     dxb = torch.empty(M, d, **bf)
+    post = tape.post_ln
+    for blk in blocks:
+        grads.bucket(blk)
+    # Every LayerNorm backward also emits the bf16 copy of the residual-stream gradient it has just updated and that
+    # gradient's column sums: the operand and the bias gradient of the linear layer whose backward comes next (c_proj
+    # of the block above / out_proj of this block) -- instead of a cast pass and a column-sum pass each.
+    ops.layernorm_bwd(stage_grads[S - 1], tape.x_out, _f32(post.weight), dx, False, M, d, grads.of(post.weight),
+                      grads.of(post.bias), dx_bf16=dxb, dx_colsum=grads.of(blocks[S - 1].mlp.c_proj.bias))
     dh = torch.empty(M, 4 * d, **bf)
     dy32 = torch.empty(M, d, **f32)
     datt = torch.empty(M, d, **bf)
@@ -302,30 +342,31 @@ def stack_backward(tape: StackTape, stage_grads: List[Optional[torch.Tensor]], g
         blk, lt = blocks[i], tape.layers[i]
         H = blk.n_head
         # ---- MLP: x_out = x1 + c_proj(gelu(c_fc(ln_2(x1)))) ------------------------------------------
-        ops.cast_bf16(dx, dxb)
         if FUSE_GELU:        # du = (dx @ W_proj) o gelu'(u) in one GEMM
             ops.linear_gelu_bwd(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), lt.u, dh)
-            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
+            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight))
         else:
             _dgrad(dxb, ops.transpose_bf16(cache.get(blk.mlp.c_proj.weight)), out_bf16=dh)
-            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight), grads.of(blk.mlp.c_proj.bias))
+            _wgrad(dxb, lt.h, grads.of(blk.mlp.c_proj.weight))
             ops.quickgelu_bwd(dh, lt.u, dh)                                    # du, in place
         _dgrad(dh, ops.transpose_bf16(cache.get(blk.mlp.c_fc.weight)), out_f32=dy32)
         _wgrad(dh, lt.xn2, grads.of(blk.mlp.c_fc.weight), grads.of(blk.mlp.c_fc.bias))
         ops.layernorm_bwd(dy32, lt.x1, _f32(blk.ln_2.weight), dx, True, M, d, grads.of(blk.ln_2.weight),
-                          grads.of(blk.ln_2.bias))
+                          grads.of(blk.ln_2.bias), dx_bf16=dxb, dx_colsum=grads.of(blk.attn.out_proj.bias))
         # ---- attention: x1 = x + out_proj(attn(in_proj(ln_1(x)))) --------------------------------------
-        ops.cast_bf16(dx, dxb)
         _dgrad(dxb, ops.transpose_bf16(cache.get(blk.attn.out_proj.weight)), out_bf16=datt)
-        _wgrad(dxb, lt.att, grads.of(blk.attn.out_proj.weight), grads.of(blk.attn.out_proj.bias))
+        _wgrad(dxb, lt.att, grads.of(blk.attn.out_proj.weight))
         q, k, v = lt.qkv[:, 0:d], lt.qkv[:, d:2 * d], lt.qkv[:, 2 * d:3 * d]
         ops.attention_bwd(q, k, v, lt.att, datt, tape.kpm, dqkv[:, 0:d], dqkv[:, d:2 * d], dqkv[:, 2 * d:3 * d], lt.lse,
                           delta, B, H, L, L)
         sg = stage_grads[i - 1] if i >= 1 else None      # ln_1 of block i IS stage i-1 (model/tfm_model.py:50-53)
         _dgrad(dqkv, ops.transpose_bf16(cache.get(blk.attn.in_proj_weight)), out_f32=dy32, residual=sg)
         _wgrad(dqkv, lt.xn, grads.of(blk.attn.in_proj_weight), grads.of(blk.attn.in_proj_bias))
+        below = blocks[i - 1].mlp.c_proj.bias if i >= 1 else None      # the next consumer of dx
         ops.layernorm_bwd(dy32, lt.x_in, _f32(blk.ln_1.weight), dx, True, M, d, grads.of(blk.ln_1.weight),
-                          grads.of(blk.ln_1.bias))
+                          grads.of(blk.ln_1.bias), dx_bf16=dxb if i >= 1 else None,
+                          dx_colsum=grads.of(below) if below is not None else None)
+        grads.reduce_bucket(blk)       # several GPUs: this block's gradients travel while the next block computes
     return dx
 
 
@@ -432,7 +473,7 @@ def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out:
     L = T + N
     dev = tape.pre_v.device
     f32 = dict(dtype=torch.float32, device=dev)
-    grads = _Grads()
+    grads = _Grads(dist)
     scale = (grad_out.detach().to(torch.float32) * (0.5 * nce_weight)).reshape(())
     b_off = ctx_dual.nce.b_off
 
@@ -527,14 +568,18 @@ def step_backward(tape: StepTape, ctx_dual: SimCtx, ctx_joint: SimCtx, grad_out:
         tape.input_grads.append(d_video.view(B, T, tape.Din))
 
     out = [grads.get(p) for p in params]
-    if dist is not None:                                           # weights are replicated: sum the ranks' gradients
-        live = [g_ for g_ in out if g_ is not None]
-        flat = torch.cat([g_.reshape(-1) for g_ in live])
-        dist.all_reduce(flat)
-        off = 0
-        for g_ in live:
-            g_.copy_(flat[off:off + g_.numel()].view_as(g_))
-            off += g_.numel()
+    if dist is not None:       # weights are replicated: sum the ranks' gradients.  The transformer blocks went out per
+        # block during the backward pass (_Grads.reduce_bucket); what is left (pre-projections, input LayerNorms,
+        # positional tables, head) goes in one flat all-reduce
+        live = [g_ for p, g_ in zip(params, out) if g_ is not None and id(p) not in grads.reduced]
+        if live:
+            flat = torch.cat([g_.reshape(-1) for g_ in live])
+            dist.all_reduce(flat)
+            off = 0
+            for g_ in live:
+                g_.copy_(flat[off:off + g_.numel()].view_as(g_))
+                off += g_.numel()
+        grads.wait()
     return out
 
 

@@ -178,7 +178,8 @@ def colsum(x, out, accumulate=True):
     out.copy_(out + s if accumulate else s)
 
 
-def layernorm_bwd(dy, x, gamma, dx, accumulate_dx, rows, d, dgamma, dbeta, L_in=None, L_out=None, l_off=0):
+def layernorm_bwd(dy, x, gamma, dx, accumulate_dx, rows, d, dgamma, dbeta, L_in=None, L_out=None, l_off=0,
+                  dx_bf16=None, dx_colsum=None):
     L_in = rows if L_in is None else L_in
     L_out = L_in if L_out is None else L_out
     r = torch.arange(rows)
@@ -193,6 +194,10 @@ def layernorm_bwd(dy, x, gamma, dx, accumulate_dx, rows, d, dgamma, dbeta, L_in=
     if dgamma is not None:
         dgamma.add_(gm.grad)
         dbeta.add_(bt.grad)
+    if dx_bf16 is not None:
+        _rows(dx_bf16)[:rows].copy_(tgt.to(BF))
+    if dx_colsum is not None:
+        dx_colsum.add_(tgt.float().sum(0))
 
 
 def l2norm_bwd(x, g, dst, accumulate, rows, d, L_in, src_stride, L_out, l_off, g_stride=None):

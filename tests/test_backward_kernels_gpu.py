@@ -88,6 +88,16 @@ def test_layernorm_bwd(rows, d, accumulate):
     assert (dx - ref_dx).abs().max().item() < 1e-4 * max(1.0, ref_dx.abs().max().item())
     assert (dgamma - 0.5 - gr.grad).abs().max().item() < 1e-3 * max(1.0, gr.grad.abs().max().item())
     assert (dbeta + 0.5 - br.grad).abs().max().item() < 1e-3 * max(1.0, br.grad.abs().max().item())
+    # fused outputs: bf16 copy of the updated dx and its column sums (accumulated into the given vector)
+    dx2 = dx0.clone()
+    dxb = torch.zeros(rows, d, dtype=torch.bfloat16, device=DEV)
+    csum = torch.full((d,), 2.0, dtype=torch.float32, device=DEV)
+    dg2, db2 = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    ops.layernorm_bwd(dy, x, gamma, dx2, accumulate, rows, d, dg2, db2, dx_bf16=dxb, dx_colsum=csum)
+    assert torch.equal(dx2, dx)
+    assert torch.equal(dxb, dx.to(torch.bfloat16))
+    ref_c = 2.0 + dx.double().sum(0)
+    assert (csum.double() - ref_c).abs().max().item() < 1e-3 * max(1.0, ref_c.abs().max().item())
 
 
 def test_layernorm_bwd_row_map():
