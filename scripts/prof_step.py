@@ -26,6 +26,8 @@ if "--hbm" in sys.argv:
     rs = torch.empty(2, Bq * S * T, dtype=torch.float32, device=dense.device)
     cs = torch.empty(2, S, B2 * N, dtype=torch.float32, device=dense.device)
     ws = torch.empty(ops.sim_workspace_bytes(g), dtype=torch.uint8, device=dense.device)
+    from temporalalignnet_b200 import loss as loss_mod
+    nce = loss_mod.prepare_nce_inputs(r.batch["start"], r.batch["end"], r.d_tpm, r.T, r.N, r.device, False, compact=False)
     for _ in range(2):
-        ops.nce_from_logits(dense, g, r.nce.posbits, r.nce.col_valid, rs, cs, ws)
+        ops.nce_from_logits(dense, g, nce.posbits, nce.col_valid, rs, cs, ws)
     torch.cuda.synchronize()

@@ -195,6 +195,61 @@ def padded_times(start_list, end_list, T: int, N: int, device):
 COMPACT_COLUMNS = os.environ.get("TAN_COMPACT_COLUMNS", "1") != "0"
 
 
+EXCH_CAP = 1022      # clips per rank the one-collective shape exchange can describe (2 + EXCH_CAP int32 = 4 KB)
+_exch_cache = {}
+
+
+def shard_exchange(B: int, N: int, n_loc, device):
+    """ONE fixed-size collective on the side stream per call: every rank contributes [B, N, n_1 .. n_B] (sentence
+    counts of its clips, zero-padded to EXCH_CAP), so that the shape agreement check and the global per-clip
+    sentence counts of the ragged-column layout cost a single 4 KB all-gather and a single host wait.
+    Returns (b_min, b_max, n_min, n_max, flat list of the sentence counts of all ranks' clips or None)."""
+    dist = _dist()
+    if dist is None:
+        return B, B, N, N, list(n_loc) if n_loc is not None else None
+    if B > EXCH_CAP:
+        b = shard_shapes(B, N, device)
+        return (*b, _host_all_gather_int(n_loc, device) if n_loc is not None else None)
+    device = torch.device(device)
+    W = dist.get_world_size()
+    cuda = device.type == "cuda"
+    key = (str(device), W)
+    ent = _exch_cache.get(key)
+    if ent is None:
+        host = torch.zeros(2 + EXCH_CAP, dtype=torch.int32)
+        recv = torch.zeros(W * (2 + EXCH_CAP), dtype=torch.int32)
+        if cuda:
+            host, recv = host.pin_memory(), recv.pin_memory()
+        # torch.empty on purpose: a zero-fill would be a kernel on the MAIN stream, which may run (after whatever is
+        # queued there) in the middle of the side stream's copy -> gather -> copy sequence below
+        ent = _exch_cache[key] = (host, recv, torch.empty(2 + EXCH_CAP, dtype=torch.int32, device=device),
+                                  torch.empty(W * (2 + EXCH_CAP), dtype=torch.int32, device=device))
+    host, recv, d_send, d_recv = ent
+    host.zero_()
+    host[0], host[1] = B, N
+    if n_loc is not None:
+        host[2:2 + B] = torch.as_tensor(n_loc, dtype=torch.int32)
+    st = _shape_streams.get(str(device))
+    if st is None:
+        st = _shape_streams[str(device)] = torch.cuda.Stream(device=device) if cuda else False
+    if st:
+        with torch.cuda.stream(st):
+            d_send.copy_(host, non_blocking=True)
+            dist.all_gather_into_tensor(d_recv, d_send)
+            recv.copy_(d_recv, non_blocking=True)
+        st.synchronize()                       # the side stream only: the main stream's queued kernels keep running
+        got = recv.view(W, 2 + EXCH_CAP)
+    else:                                      # gloo on CPU tensors (host tests)
+        outs = [torch.empty_like(host) for _ in range(W)]
+        dist.all_gather(outs, host.clone())
+        got = torch.stack(outs)
+    bs, ns = got[:, 0].tolist(), got[:, 1].tolist()
+    n_glob = None
+    if n_loc is not None and min(bs) == max(bs):
+        n_glob = got[:, 2:2 + B].reshape(-1).tolist()
+    return min(bs), max(bs), min(ns), max(ns), n_glob
+
+
 def _host_all_gather_int(vec, device):
     """All-gather a short list of ints over the ranks through a SIDE stream (see shard_shapes) -> flat python list."""
     dist = _dist()
@@ -215,8 +270,11 @@ def _host_all_gather_int(vec, device):
     return torch.cat(outs).tolist()
 
 
+_compact_cache = {}
+
+
 def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, device, shard: bool,
-                       pos_fn=None, padded=None, compact: bool = False) -> NceInputs:
+                       pos_fn=None, padded=None, compact: bool = False, n_glob=None) -> NceInputs:
     """Targets of the `--model init` recipe: bit (b, t, n) = real sentence and start <= t < end
     (train/loss.py:26-41,:80-85), built on the device by tan_pos_from_time; the column-valid mask
     (~text_padding_mask, :235) is all-gathered over ranks with `shard` so that columns are global.
@@ -243,20 +301,31 @@ def prepare_nce_inputs(start_list, end_list, text_padding_mask, T: int, N: int, 
     if not (compact and COMPACT_COLUMNS):
         return NceInputs(posbits, valid_g, N, T, b_off, B_glob)
     import numpy as np
-    n_loc = [min(len(s_), N) for s_ in start_list]
-    n_glob = n_loc if dist is None else _host_all_gather_int(n_loc, device)
-    off = np.zeros(B_glob + 1, np.int32)
-    np.cumsum(np.asarray(n_glob, np.int64), out=off[1:])
-    src = np.concatenate([b * N + np.arange(n, dtype=np.int64) for b, n in enumerate(n_glob)]) if off[-1] else \
-        np.zeros(0, np.int64)
-    pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
-    col_off = torch.from_numpy(off)
-    col_src = torch.from_numpy(src)
-    if pin:
-        col_off, col_src = col_off.pin_memory(), col_src.pin_memory()
-    col_off, col_src = col_off.to(device, non_blocking=True), col_src.to(device, non_blocking=True)
-    covered = torch.zeros(B_glob * N, dtype=torch.bool, device=device)
-    covered[col_src] = True
+    if n_glob is None:
+        n_loc = [min(len(s_), N) for s_ in start_list]
+        n_glob = n_loc if dist is None else _host_all_gather_int(n_loc, device)
+    n_glob = [min(int(n_), N) for n_ in n_glob]
+    # the layout tensors only depend on (sentence counts, N, device): batches that repeat them (fixed-length
+    # loaders, benchmarks) reuse the device copies
+    ckey = (tuple(n_glob), N, str(device))
+    ent = _compact_cache.get(ckey)
+    if ent is None:
+        off = np.zeros(B_glob + 1, np.int32)
+        np.cumsum(np.asarray(n_glob, np.int64), out=off[1:])
+        src = np.concatenate([b * N + np.arange(n, dtype=np.int64) for b, n in enumerate(n_glob)]) if off[-1] else \
+            np.zeros(0, np.int64)
+        pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
+        col_off = torch.from_numpy(off)
+        col_src = torch.from_numpy(src)
+        if pin:
+            col_off, col_src = col_off.pin_memory(), col_src.pin_memory()
+        col_off, col_src = col_off.to(device, non_blocking=True), col_src.to(device, non_blocking=True)
+        covered = torch.zeros(B_glob * N, dtype=torch.bool, device=device)
+        covered[col_src] = True
+        if len(_compact_cache) > 8:
+            _compact_cache.clear()
+        ent = _compact_cache[ckey] = (col_off, col_src, covered)
+    col_off, col_src, covered = ent
     poison = (valid_g.bool() & ~covered).any()
     return NceInputs(posbits, valid_g.index_select(0, col_src).contiguous(), N, T, b_off, B_glob, col_off=col_off,
                      col_src=col_src, poison=poison)
@@ -518,10 +587,15 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     device = logits_dual.device
     shard = (_dist() is not None) if shard_batch is None else bool(shard_batch)
     dist = _dist() if shard else None
-    if dist is not None and SHARD_CHECK:
+    n_glob = None
+    will_compact = (COMPACT_COLUMNS and not (learn or thr > 0 or head) and N <= 64 and isinstance(logits_dual, LazyLogits)
+                    and isinstance(logits_joint, LazyLogits))
+    if dist is not None and (SHARD_CHECK or will_compact):
         # the all-gathers below assume one (B_loc, N) on every rank; with real data N is each rank's own
-        # pad_sequence length -- fail loudly instead of hanging in NCCL or mis-indexing columns
-        b_min, b_max, n_min, n_max = shard_shapes(B, N, device)
+        # pad_sequence length -- fail loudly instead of hanging in NCCL or mis-indexing columns.  The same 4 KB
+        # exchange carries every clip's sentence count for the ragged-column layout.
+        n_loc = [min(len(s_), N) for s_ in input_data['start']] if will_compact else None
+        b_min, b_max, n_min, n_max, n_glob = shard_exchange(B, N, n_loc, device)
         if b_min != b_max or n_min != n_max:          # the same verdict on every rank: nobody enters a collective alone
             raise TanError(f"sharded get_loss: ranks disagree on the batch shape (this rank B={B}, N={N}; ranks have "
                            f"B {b_min}..{b_max}, N {n_min}..{n_max}).  Pad the text inputs with "
@@ -530,10 +604,8 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     padded = (input_data['start_pad'], input_data['end_pad']) if 'start_pad' in input_data else None
     # ragged columns (padded sentences never computed): the plain recipe on fused logits; the flag branches index
     # [B*N]-shaped vectors by padded column and the N > 64 gradient path has no ragged variant
-    compact = (not (learn or thr > 0 or head) and N <= 64 and isinstance(logits_dual, LazyLogits)
-               and isinstance(logits_joint, LazyLogits))
     nce = prepare_nce_inputs(input_data['start'], input_data['end'], text_padding_mask, T, N, device, shard, padded=padded,
-                             compact=compact)
+                             compact=will_compact, n_glob=n_glob)
     loss_dict = {}
     # training step: the forward ran with a tape (model.enable_autograd) -> the returned loss carries ONE autograd
     # node whose backward is the hand-written backward pass (train.py)
