@@ -17,6 +17,14 @@ __global__ void k(float* out, int iters) {
       if (MODE == 1) { __nv_bfloat162 v = __floats2bfloat162_rn(a[i], a[(i + 1) & 7]); acc ^= *reinterpret_cast<unsigned*>(&v); a[i] += 1e-3f; }
       if (MODE == 2) a[i] = fmaxf(a[i], a[(i + 3) & 7] * 0.999f);
       if (MODE == 3) a[i] = fmaf(a[i], 0.999f, 0.001f);
+      // the softmax inner pattern: 2 x (ffma, ex2, fadd) + one pack of the pair -- with cvt.rn.bf16x2 (MODE 4) or with
+      // integer rounding + prmt (MODE 5); ops counted = ex2 (2 per i)
+      if (MODE == 4 || MODE == 5) {
+        const float p0 = ex2(fmaf(a[i], 0.999f, -0.5f)), p1 = ex2(fmaf(a[(i + 1) & 7], 0.998f, -0.25f));
+        a[i] = (p0 + p1) - 1.5f;
+        if (MODE == 4) { __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1); acc ^= *reinterpret_cast<unsigned*>(&v); }
+        else { acc ^= __byte_perm(__float_as_uint(p0) + 0x8000u, __float_as_uint(p1) + 0x8000u, 0x7632); }
+      }
     }
   }
   float s = 0;
@@ -42,4 +50,5 @@ void run(const char* name, int opsPerIter) {
            ops / (ms * 1e-3) / sms / (clk * 1e3), clk / 1e3);
   }
 }
-int main() { run<0>("ex2", 1); run<1>("cvt.bf16x2", 1); run<2>("fmax+fmul", 1); run<3>("ffma", 1); return 0; }
+int main() { run<0>("ex2", 1); run<1>("cvt.bf16x2", 1); run<2>("fmax+fmul", 1); run<3>("ffma", 1);
+  run<4>("2ex2+cvt", 2); run<5>("2ex2+prmt", 2); return 0; }

@@ -29,6 +29,12 @@ stall = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued'
 data = [r for r in rows[hi + 1:] if len(r) > si and r[si].isdigit()]
 tot = sum(int(r[si]) for r in data)
 print("total samples", tot)
+agg = {}
+for r in data:
+    for i in stall:
+        if int(r[i]) > 0:
+            agg[hdr[i][6:]] = agg.get(hdr[i][6:], 0) + int(r[i])
+print("stall reasons, whole kernel: " + ", ".join(f"{k} {100 * v / max(1, sum(agg.values())):.1f}%" for k, v in sorted(agg.items(), key=lambda kv: -kv[1])))
 for idx, r in enumerate(data):
     r.append(idx)
 for r in sorted(data, key=lambda r: -int(r[si]))[:n]:

@@ -10,6 +10,8 @@
 namespace tanb {
 
 __device__ long long* g_gemm_trace = nullptr;
+static long long* g_trace_host = nullptr;      // the same pointer for kernels that take it as an argument
+long long* debug_trace_ptr() { return g_trace_host; }
 
 static thread_local char g_err[512] = "";
 
@@ -182,6 +184,7 @@ extern "C" int tan_debug_set_trace(void* device_buffer) {
   TAN_CHECK(tan_device_check());
   long long* p = static_cast<long long*>(device_buffer);
   TAN_CUDA(cudaMemcpyToSymbol(g_gemm_trace, &p, sizeof(p)));
+  g_trace_host = p;
   return TAN_OK;
 }
 

@@ -20,6 +20,8 @@ typedef __nv_bfloat16 bf16;
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+// development aid (tan_debug_set_trace): device buffer for per-CTA clock stamps, or null
+long long* debug_trace_ptr();
 // per-device cudaFuncAttributeMaxDynamicSharedMemorySize (capi.cu)
 int set_max_dyn_smem(const void* kernel, int bytes);
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency).

@@ -218,7 +218,10 @@ def _attn_ref(q, k, v, kpm, B, H, Lq, Lk):
     return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Lq, d)
 
 
-@pytest.mark.parametrize("B,H,L", [(2, 8, 32), (3, 8, 72), (2, 8, 256), (2, 12, 288), (1, 8, 1152), (4, 2, 37)])
+# (40, 8, 256), (24, 8, 288), (5, 8, 600): more (clip, head, query-tile pair) tasks than SMs, so every persistent CTA
+# walks several tasks (pipelines running across task boundaries, pairs with and without a second tile)
+@pytest.mark.parametrize("B,H,L", [(2, 8, 32), (3, 8, 72), (2, 8, 256), (2, 12, 288), (1, 8, 1152), (4, 2, 37),
+                                   (40, 8, 256), (24, 8, 288), (5, 8, 600), (3, 4, 129)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_self_attention(B, H, L, masked):
     ops = _ops()
@@ -235,6 +238,29 @@ def test_self_attention(B, H, L, masked):
     # bf16 P and bf16 output: abs error ~ 2^-8 of the output scale
     assert (out.float() - ref).abs().max().item() < 2e-2 * max(ref.abs().max().item(), 0.1)
     assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2
+
+
+def test_attention_rising_scores_rescale_the_accumulator():
+    # keys whose scores grow along the sequence: every later key block exceeds the running reference maximum by far
+    # more than the lazy-rescale slack of 2^8, so the O accumulator in TMEM is rescaled at every block
+    ops = _ops()
+    B, H, L = 20, 8, 520
+    d = H * 64
+    qkv = _rand(B * L, 3 * d, seed=23)
+    ramp = torch.linspace(0.2, 3.0, L, device=DEV).repeat(B)[:, None]
+    qkv[:, :d] += 1.0                                                  # a common query direction ...
+    qkv[:, d:2 * d] = 3.0 * ramp + 0.3 * qkv[:, d:2 * d]               # ... along which the keys grow: score ~ 24 ramp
+    qkv = qkv.to(torch.bfloat16)
+    out = torch.empty(B * L, d, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(B, H, (L + 63) // 64 * 64, dtype=torch.float32, device=DEV)
+    ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, out, B, H, L, L, lse=lse)
+    ref = _attn_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, B, H, L, L)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 1e-2
+    qh = qkv[:, :d].float().view(B, L, H, 64).transpose(1, 2)
+    kh = qkv[:, d:2 * d].float().view(B, L, H, 64).transpose(1, 2)
+    lse_ref = torch.logsumexp(qh @ kh.transpose(-1, -2) / 8.0, -1) * 1.4426950408889634     # log2 domain
+    assert (lse[:, :, :L] - lse_ref).abs().max().item() < 2e-3 * lse_ref.abs().max().item() + 1e-2
+    assert torch.isinf(lse[:, :, L:]).all()
 
 
 def test_cross_attention_and_all_masked_row_is_nan():
