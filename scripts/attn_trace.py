@@ -1,5 +1,4 @@
-"""Per-CTA timeline of one tan_attention_bf16 launch (tan_debug_set_trace; slot layout: csrc/attention_pp.cu).
-usage: attn_trace.py B H L"""
+"""Per-CTA timeline of one tan_attention_bf16 launch (tan_debug_set_trace).  usage: B H L"""
 import os, sys
 import numpy as np
 import torch
@@ -13,28 +12,27 @@ run = lambda: ops.attention(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], None, o
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-NCTA, SLOTS = 148, 256
-tr = torch.zeros(NCTA * SLOTS, dtype=torch.int64, device="cuda")
+tr = torch.zeros(512 * 128, dtype=torch.int64, device="cuda")
 _lib.check(_lib.lib().tan_debug_set_trace(tr.data_ptr()))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush.zero_()
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
 e0.record(); run(); e1.record()
 torch.cuda.synchronize()
 _lib.check(_lib.lib().tan_debug_set_trace(None))
-t = tr.cpu().numpy().reshape(NCTA, SLOTS)
+t = tr.cpu().numpy().reshape(512, 128)
 t = t[t[:, 1] != 0]
 print(f"B={B} H={H} L={L}: event time {e0.elapsed_time(e1) * 1e3:.1f} us, traced CTAs {len(t)}")
 rel = lambda col: (t[:, col] - t[:, 1])
 print(f"prologue done (clk): median {np.median(rel(2)):.0f}   CTA lifetime: median {np.median(rel(3)):.0f} max {rel(3).max():.0f}")
-names = ["K_iss", "V_iss", "QK_A", "QK_B", "prdyA", "PV_A", "prdyB", "PV_B", "sfulA", "SregA", "PstgA", "sfulB", "SregB",
-         "PstgB", "epiA", "epiB"]
-print("block  " + " ".join(f"{n:>6s}" for n in names))
-for s in range(14):
+names = ["K_issued", "V_issued", "QK_issued", "p_ready_seen", "PV_issued", "s_full_seen", "S_in_regs", "P_staged"]
+nb = (L + 63) // 64
+for g in range(min(10, 2 * nb)):
     vals = []
-    for k in range(16):
-        c = 8 + 16 * s + k
+    for k in range(8):
+        c = 8 + 10 * g + k
         ok = t[:, c] != 0
         vals.append(np.median(t[ok][:, c] - t[ok][:, 1]) if ok.any() else float("nan"))
-    if all(np.isnan(v) for v in vals):
-        break
-    print(f"{s:5d}  " + " ".join(f"{v:6.0f}" for v in vals))
+    print(f"block {g}: " + "  ".join(f"{n}={v:7.0f}" for n, v in zip(names, vals)))
+# first-wave vs later-wave CTAs
+first = t[:, 0] <= np.sort(t[:, 0])[min(len(t) - 1, 295)]
+print(f"first-wave CTAs lifetime median {np.median(rel(3)[first]):.0f}, later {np.median(rel(3)[~first]) if (~first).any() else float('nan'):.0f}")

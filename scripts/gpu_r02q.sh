@@ -1,7 +1,5 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-TAN_ATT_FLAGS=0 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attention_kernel --launch-skip 3 --launch-count 1 -f -o gpurun_out/r02q_attn2 python scripts/attn_time.py 256 8 256 > gpurun_out/r02q_ncu2.log 2>&1
-tail -2 gpurun_out/r02q_ncu2.log
-python scripts/ncu_top.py gpurun_out/r02q_attn2.ncu-rep 30 > gpurun_out/r02q_attn2_summary.txt 2>&1
-head -40 gpurun_out/r02q_attn2_summary.txt
+for v in _old _oldw ""; do echo "== timings variant '$v'"; TAN_LIB_PATH=$PWD/temporalalignnet_b200/libtan_b200$v.so timeout 200 python scripts/attn_time.py 256 8 256 256 8 288 32 8 256 32 8 288 32 12 1024 32 12 1152 128 8 512 128 8 576 64 8 64 64 8 72 2>&1 | tail -10; done
+echo "== attention kernel tests (old kernel, plain try_wait)"; TAN_LIB_PATH=$PWD/temporalalignnet_b200/libtan_b200_oldw.so timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_backward_kernels_gpu.py -q -x -p no:cacheprovider -k "attention" 2>&1 | tail -3

@@ -1,8 +1,12 @@
+// NOT BUILT, NOT SHIPPED: the persistent ping-pong attention kernel of round 2, measured slower than attention.cu on
+// every benchmarked shape and rejected (profiles/r02q_attention_pingpong_rejected.txt).  Kept as the record of the
+// experiment; it was compiled in place of csrc/attention.cu (non-rdc object, see the setmaxnreg note below).
+//
 // tan_attention_bf16: multi-head softmax attention core on tcgen05 tensor cores, head_dim 64, arbitrary
 // key-padding mask, Lq != Lk allowed (cross-attention).  Replaces torch's nn.MultiheadAttention core
 // (model/tfm_model.py:30-32 of the reference: softmax(q k^T / 8 + key_padding_mask) v per head).
 //
-// PERSISTENT kernel, one CTA per SM, 384 threads = 3 warpgroups.  A task is (clip, head, PAIR of 128-query tiles A | B); a CTA
+// PERSISTENT kernel, one CTA per SM, 640 threads = 5 warpgroups.  A task is (clip, head, PAIR of 128-query tiles A | B); a CTA
 // walks its tasks (task = blockIdx.x + i * gridDim.x) and, inside each, the 128-key blocks.  Every pipeline keeps
 // running across task boundaries (flat block counter s = i * nb + j), so TMEM allocation, barrier set-up and the
 // first-load latency are paid once per CTA, and a task's last PV / output epilogue overlaps the next task's
@@ -16,12 +20,13 @@
 //               anywhere) as soon as P_X is staged.  The two tiles run in PING-PONG, tile B half a softmax behind
 //               tile A: the MMAs, barrier round trips, TMEM loads and the output epilogue of one tile execute
 //               under the exponentials of the other.
-//   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: thread = one query row (TMEM lane), so row max /
-//               row sum are thread-local; the 128 scores of the row come from TMEM with four tcgen05.ld.x32 and
-//               stay in registers (the warpgroups trade registers with setmaxnreg: 72 for the TMA / MMA
-//               warpgroup, 216 for the two softmax warpgroups), P = exp2(S - m) goes back to shared memory as the
-//               bf16 A operand of PV (two 128B-swizzled K-major half tiles of 64 keys, the layout TMA would have
-//               produced).
+//   warps 4-11  softmax of tile A, warps 12-19 softmax of tile B, TWO threads per query row (TMEM lane): thread
+//               (half hh) owns the key columns [64 hh, 64 hh + 64) of every block -- 64 scores in registers from two
+//               tcgen05.ld.x32, four softmax warps per scheduler (the warpgroups trade registers with setmaxnreg:
+//               64 for the TMA / MMA warpgroup, 104 for the four softmax warpgroups; the sum must stay within the 640 x 96 registers of the launch).  The halves of a row agree on
+//               the block maximum through shared memory and a 64-thread named barrier; P = exp2(S - m) goes back to
+//               shared memory as the bf16 A operand of PV (each half writes one 128-byte row of ITS 64-key half
+//               tile, 128B-swizzled K-major: the layout TMA would have produced).
 // TMEM (512 columns): S_A [0,128), S_B [128,256), O_A [256,320), O_B [320,384).  O ACCUMULATES IN TMEM across the
 // key blocks and is read once per task.  The reference max m of a row is only raised when a block's maximum
 // exceeds it by more than 8 (log2 domain, i.e. P <= 256: harmless for bf16 P and fp32 sums); only then the warp
@@ -41,12 +46,13 @@ namespace tanb {
 
 constexpr int kPpBQ = 128;                     // query rows per tile (UMMA M)
 constexpr int kPpBK = 128;                     // keys per block (UMMA N of QK, K of PV)
-constexpr int kPpThreads = 384;
+constexpr int kPpThreads = 640;                // 5 warpgroups: producer / MMA issuers, 4 x softmax
+constexpr int kPpSoftmaxRegs = 104;            // setmaxnreg: 64 for warpgroup 0, 104 for the softmax warpgroups (640 x 96 at launch)
 constexpr int kPpTile = 128 * 128;             // bytes: 128 rows x 64 bf16 (16 KB): a Q tile, a K / V block, half a P tile
 constexpr int kPpStages = 3;
-constexpr int kPpMaskWords = 128;              // mask bits for Lk <= 4096
+constexpr int kPpMaskWords = 64;               // mask bits for Lk <= 2048 (longer: per-block ballots)
 constexpr int kPpSmem = 2 * 2 * kPpTile /*Q pair x 2*/ + 2 * kPpStages * kPpTile /*K, V rings*/ +
-                        2 * 2 * kPpTile /*P_A, P_B*/ + 512 /*barriers*/ + 2 * kPpMaskWords * 4;
+                        2 * 2 * kPpTile /*P_A, P_B*/ + 512 /*barriers*/ + 2 * kPpMaskWords * 4 + 2 * 1024 /*row exchange*/;
 static_assert(kPpSmem <= 227 * 1024, "one CTA per SM");
 
 // warpgroup-wide register reallocation (all 128 threads of the warpgroup execute it)
@@ -97,7 +103,6 @@ struct PpArgs {
   int npairs;               // query-tile pairs per (clip, head)
   int ntasks;               // B * H * npairs
   long long* trace;         // development aid (tan_debug_set_trace): 256 clock stamps per CTA, or null
-  int flags;                // bit 0: start tile B half a softmax behind tile A
 };
 
 // Trace slots of a CTA: 0 globaltimer, 1 start, 2 prologue done, 3 exit; flat block s < 14 at 8 + 16 s:
@@ -107,11 +112,34 @@ struct PpArgs {
 // Bounded wait of this kernel: on a time-out (a protocol bug) the waiter leaves (site, value, parity) in slot
 // 200 + warp of the CTA's trace record -- readable after the trap when the trace buffer is mapped host memory --
 // and traps (surfacing as a CUDA error instead of a hung GPU).
+#ifndef TAN_ATT_WAIT
+#define TAN_ATT_WAIT 1      // 0: try_wait with a suspend-time hint, 1: plain try_wait, 2: test_wait spin (A/B builds)
+#endif
+__device__ __forceinline__ bool pp_poll(uint64_t* bar, uint32_t parity) {
+#if TAN_ATT_WAIT == 0
+  return mbar_try_wait_hint(bar, parity);
+#elif TAN_ATT_WAIT == 1
+  return mbar_try_wait(bar, parity);
+#else
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+#endif
+}
 __device__ __forceinline__ void pp_wait(uint64_t* bar, uint32_t parity, long long* trace, int site, int val) {
-  if (mbar_try_wait_hint(bar, parity)) return;
+  if (pp_poll(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait_hint(bar, parity)) {
-    if (clock64() - t0 > (1ll << 29)) {
+  int spins = 0;
+  while (!pp_poll(bar, parity)) {
+    if ((++spins & 255) == 0 && clock64() - t0 > (1ll << 29)) {
       if (trace != nullptr) {
         trace[static_cast<int64_t>(blockIdx.x) * 256 + 232 + (threadIdx.x >> 5)] =
             (static_cast<long long>(site) << 40) | (static_cast<long long>(val & 0xffffff) << 8) | parity;
@@ -146,14 +174,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* v_full = bars + 10;        // [3]
   uint64_t* v_empty = bars + 13;       // [3]
   uint64_t* s_full = bars + 16;        // [A | B] QK of the tile's current block has completed
-  uint64_t* p_ready = bars + 18;       // [A | B] count 4: S consumed, P staged (O rescaled if needed)
+  uint64_t* p_ready = bars + 18;       // [A | B] count 8 (softmax warps of the tile): P staged (O rescaled if needed)
   uint64_t* pv_done = bars + 20;       // [A | B] PV of the tile's current block has completed: P free, O stable
-  uint64_t* o_free = bars + 22;        // [A | B] count 4: the task's O has been read out of TMEM
-  uint64_t* mask_free = bars + 24;     // [2] by task parity, count 8: every softmax warp is done with the task
-  uint64_t* s_free = bars + 26;        // [A | B] count 4: the block's scores are in registers, S may be overwritten
-  uint64_t* half_a = bars + 28;        // count 4: tile A is half way through the exponentials of the CTA's first block
+  uint64_t* o_free = bars + 22;        // [A | B] count 8: the task's O has been read out of TMEM
+  uint64_t* mask_free = bars + 24;     // [2] by task parity, count 16: every softmax warp is done with the task
+  uint64_t* s_free = bars + 26;        // [A | B] count 8: the block's scores are in registers, S may be overwritten
+  uint64_t* turn = bars + 28;          // [A | B] count 8: the OTHER tile has finished a block's exponentials, this one may start
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(bars + 64);     // [2 task parities][kPpMaskWords]
+  uint8_t* s_xch = reinterpret_cast<uint8_t*>(s_mask + 2 * kPpMaskWords);   // [tile][1 KB]: block maxima bf16 [parity][half][row], or sums fp32 [half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* const tr = (a.trace != nullptr && lane == 0) ? a.trace + static_cast<int64_t>(blockIdx.x) * 256 : nullptr;
@@ -174,11 +203,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tma_prefetch_desc(&tmV);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 2);
-        mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 4);
-        mbar_init(&mask_free[i], 8);
-        mbar_init(&s_free[i], 4);
+        mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 8); mbar_init(&pv_done[i], 1); mbar_init(&o_free[i], 8);
+        mbar_init(&mask_free[i], 16);
+        mbar_init(&s_free[i], 8);
       }
-      mbar_init(half_a, 4);
+      mbar_init(&turn[0], 8);
+      mbar_init(&turn[1], 8);
       for (int i = 0; i < kPpStages; ++i) {
         mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 2); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 2);
       }
@@ -210,7 +240,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // each role's code must be DOMINATED by its setmaxnreg (ptxas allocates a region with the count of the
   // instruction that dominates it; after a merge point it would fall back to the smaller one)
   if (warp < 4) {
-  reg_dealloc<72>();
+  reg_dealloc<64>();
   if (warp == 0) {
     // ===== TMA producer (+ the clip's key mask as bits) =====
     for (int i = 0; i < ncta; ++i) {
@@ -322,9 +352,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j == 0) ++tsk;
     };
 
-    // tile B starts half a softmax behind tile A (its first QK waits until tile A is half way through its first
-    // exponentials): one warpgroup is then in its TMEM-load / max / epilogue phase while the other owns the MUFU pipe
-    if (X == 1 && (a.flags & 1) && S > 0) pp_wait(half_a, 0, a.trace, 11, 0);
     int prev = -1;
     for (int s = 0; s < S; ++s) {
       if (X == 1 && !has_b(pair_of(s / nb))) {
@@ -355,17 +382,56 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (prev >= 0) issue_pv(prev);
   }
   } else {
-    reg_alloc<216>();
-    // ===== softmax / output: warps 4..7 tile A, warps 8..11 tile B =====
-    const int X = (warp - 4) >> 2;
+    reg_alloc<kPpSoftmaxRegs>();
+    // ===== softmax / output: warps 4..11 tile A, warps 12..19 tile B; TWO threads per query row =====
+    // Thread (quarter, lane) of half hh owns row quarter * 32 + lane and the key columns [64 hh, 64 hh + 64) of
+    // every block: four softmax warps per scheduler instead of two (the two-warp version spent a third of a block
+    // in its TMEM-load / mask / maximum phase with the MUFU pipe idle, profiles/r02q), 64 scores in registers
+    // instead of 128.  The halves of a row exchange their block maxima (and, once per task, their sums) through
+    // shared memory and a 64-thread named barrier per (tile, quarter).
+    const int X = (warp - 4) >> 3;
+    const int hh = ((warp - 4) >> 2) & 1;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may address
     const int row = quarter * 32 + lane;               // query row inside the tile = TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t t_s = t_lane + X * 128;
-    const uint32_t t_o = t_lane + 256 + X * 64;
-    uint8_t* sPx = sP + X * 2 * kPpTile;
+    const uint32_t t_s = t_lane + X * 128 + hh * 64;
+    const uint32_t t_o = t_lane + 256 + X * 64 + hh * 32;
+    uint8_t* sPh = sP + (X * 2 + hh) * kPpTile;        // this half's 64 keys = one 128-byte row of its half tile
+    bf16* xmax = reinterpret_cast<bf16*>(s_xch + X * 1024);       // [parity][half][row]
+    float* xsum = reinterpret_cast<float*>(s_xch + X * 1024);     // [half][row] (same bytes, used between tasks)
+    const int pair_bar = 1 + X * 4 + quarter;          // named barrier of the two warps that share these rows
     const float sl2 = 0.125f * 1.4426950408889634f;    // 1/sqrt(64) folded with log2(e)
     uint32_t cnt = 0;                                  // blocks of this tile processed so far
+    uint32_t tcnt = 0;                                 // turns at the MUFU pipe taken so far (incl. the passed ones)
+    // PING-PONG of the exponentials: the tiles take strict turns A B A B ... at the MUFU pipe (turn[X] = the other
+    // tile has finished its block).  Left alone, the two tiles fall into lock step -- every warp in the same phase,
+    // the MUFU pipe idle during all TMEM loads / maxima / stores / barrier round trips (profiles/r02q); with the
+    // turns one tile's exponentials run under the other tile's everything-else.  A tile without work (no tile B in
+    // the task, no real rows in the warp) still passes its turns.
+    auto take_turn = [&]() {
+      if (X == 1 || tcnt > 0) pp_wait(&turn[X], (X == 1 ? tcnt : tcnt - 1) & 1, a.trace, 17, tcnt * 2 + X);
+    };
+    auto pass_turn = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&turn[X ^ 1]);
+      ++tcnt;
+    };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+    // the row's block maximum over both halves, as the SAME bf16-rounded value in both (any reference close to the
+    // maximum serves the softmax; the halves must only agree on it).  Double buffered by block parity.
+    auto row_max = [&](float v, uint32_t par) {
+      const bf16 mine = __float2bfloat16_rn(v);
+      xmax[(par * 2 + hh) * 128 + row] = mine;
+      pair_sync();
+      return fmaxf(__bfloat162float(mine), __bfloat162float(xmax[(par * 2 + (hh ^ 1)) * 128 + row]));
+    };
+    auto row_sum = [&](float v) {                      // once per task, no block exchange in flight
+      xsum[hh * 128 + row] = v;
+      pair_sync();
+      const float other = xsum[(hh ^ 1) * 128 + row];
+      pair_sync();                                     // read before the next task's maxima reuse the bytes
+      return v + other;
+    };
 
     for (int i = 0; i < ncta; ++i) {
       int b, h, qp;
@@ -373,6 +439,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int tp = i & 1;
       pp_wait(&q_full[tp], (i >> 1) & 1, a.trace, 12, i * 2 + X);   // mask words visible; waited for by EVERY warp in
       if (X == 1 && !has_b(qp)) {                          // EVERY task: a skipped phase would alias the parity
+        for (int j = 0; j < nb; ++j) {
+          take_turn();
+          pass_turn();
+        }
         if (lane == 0) mbar_arrive(&mask_free[tp]);
         continue;
       }
@@ -380,110 +450,110 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool mask_in_smem = nb * 4 <= kPpMaskWords;
       const uint8_t* mb = a.kpm != nullptr ? a.kpm + static_cast<int64_t>(b) * a.Lk : nullptr;
       const int q0 = qp * 2 * kPpBQ + X * kPpBQ;
-      const bool live = q0 + quarter * 32 < a.Lq;      // warp-uniform: this warp owns at least one real query row
-      float m_ref = -INFINITY, l_run = 0.f;
+      const bool live = q0 + quarter * 32 < a.Lq;      // warp-uniform: this warp pair owns at least one real query row
+      float m_ref = -INFINITY, l_run = 0.f;            // l_run: this half's share of the row sum
 
       for (int j = 0; j < nb; ++j) {
         pp_wait(&s_full[X], cnt & 1, a.trace, 13, (i * nb + j) * 2 + X);
         tc_fence_after();
-        long long* const trw = quarter == 0 ? tr : nullptr;
+        long long* const trw = (quarter == 0 && hh == 0) ? tr : nullptr;
         const int s = i * nb + j;
         pp_trace(trw, s, 8 + 3 * X);
         if (live) {
-          // one instance per number of 32-key chunks that hold a real key (4 except in a sequence's last block): a
-          // chunk without a real key is never touched (no fill, no exponentials, no P -- the PV MMA stops at the last
-          // real key), and the full block has no chunk predicates at all
+          // one instance per number of 32-key chunks of THIS half that hold a real key (2 except in a sequence's
+          // last block): a chunk without a real key is never touched (no exponentials, no P -- the PV MMA stops at
+          // the last real key)
           auto block = [&](auto nch_c) {
-          constexpr int nch = decltype(nch_c)::value;
-          uint32_t r[nch][32];
+            constexpr int nch = decltype(nch_c)::value;
+            uint32_t r[nch > 0 ? nch : 1][32];
 #pragma unroll
-          for (int c4 = 0; c4 < nch; ++c4) tmem_ld_32x32(t_s + c4 * 32, r[c4]);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[X]);      // the next block's QK may overwrite S
-          pp_trace(trw, s, 9 + 3 * X);
-          // key mask (warp-uniform words, bit set = ignore key) and row maximum, chunk by chunk
-          float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            for (int c2 = 0; c2 < nch; ++c2) tmem_ld_32x32(t_s + c2 * 32, r[c2]);
+            if (nch > 0) tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[X]);    // the next block's QK may overwrite S
+            pp_trace(trw, s, 9 + 3 * X);
+            // key mask (warp-uniform words, bit set = ignore key) and this half's row maximum
+            float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int c4 = 0; c4 < nch; ++c4) {
-            {
+            for (int c2 = 0; c2 < nch; ++c2) {
               uint32_t w;
               if (mask_in_smem) {
-                w = mk[4 * j + c4];
+                w = mk[4 * j + 2 * hh + c2];
               } else {
-                const int key = j * kPpBK + c4 * 32 + lane;
+                const int key = j * kPpBK + (2 * hh + c2) * 32 + lane;
                 w = __ballot_sync(0xffffffffu, key >= a.Lk || (mb != nullptr && mb[key] != 0));
               }
               if (w != 0u) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                  if ((w >> c) & 1u) r[c4][c] = 0xff800000u;           // -inf
+                  if ((w >> c) & 1u) r[c2][c] = 0xff800000u;           // -inf
               }
 #pragma unroll
               for (int c = 0; c < 32; c += 2)
-                mxa[(c >> 1) & 3] = fmaxf(mxa[(c >> 1) & 3], fmaxf(__uint_as_float(r[c4][c]), __uint_as_float(r[c4][c + 1])));
+                mxa[(c >> 1) & 3] = fmaxf(mxa[(c >> 1) & 3], fmaxf(__uint_as_float(r[c2][c]), __uint_as_float(r[c2][c + 1])));
             }
-          }
-          const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;      // sl2 > 0: -inf stays -inf
-          // lazy reference max: raise it only when this block exceeds it by more than 2^8
-          const bool need = (j == 0) ? (mx > m_ref) : (mx > m_ref + 8.0f);
-          if (j > 0 && __any_sync(0xffffffffu, need)) {
-            // rescale this warp's rows of O (and l) to the new reference; the previous PV must have completed
-            pp_wait(&pv_done[X], (cnt - 1) & 1, a.trace, 14, (i * nb + j) * 2 + X);
-            tc_fence_after();
-            const float alpha = need ? fast_exp2(m_ref - mx) : 1.f;    // m_ref = -inf -> 0 (O and L are 0 then)
-            pp_rescale(t_o, alpha);
-            l_run *= alpha;
-            if (need) m_ref = mx;
-          } else if (need) {
-            m_ref = mx;                                // first block of the task
-          }
-          const float nm = (m_ref == -INFINITY) ? 0.f : -m_ref;
-          // all exponentials first, packed in registers: the wait for the P buffer (the previous block's PV, a barrier
-          // round trip through the MMA issuer of ~2 k clk after that block's p_ready) comes AFTER them, right before
-          // the first store, so the round trip hides behind this block's TMEM load, maximum and exponentials
-          uint32_t pk[nch][16];
-          float ls0 = 0.f, ls1 = 0.f;
-#pragma unroll
-          for (int c4 = 0; c4 < nch; ++c4) {
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(r[c4][2 * c]), sl2, nm));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(r[c4][2 * c + 1]), sl2, nm));
-              const float p2 = fast_exp2(fmaf(__uint_as_float(r[c4][2 * c + 2]), sl2, nm));
-              const float p3 = fast_exp2(fmaf(__uint_as_float(r[c4][2 * c + 3]), sl2, nm));
-              ls0 += p0 + p1;
-              ls1 += p2 + p3;
-              pk[c4][c] = pack_bf16x2(p0, p1);         // keys 2c, 2c+1 of the chunk
-              pk[c4][c + 1] = pack_bf16x2(p2, p3);
+            const float mx_own = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * sl2;   // sl2 > 0: -inf stays -inf
+            const float mx = row_max(mx_own, cnt & 1);                       // the row's maximum over the block
+            // lazy reference max: raise it only when this block exceeds it by more than 2^8 (both halves of a row
+            // see the same mx and m_ref, so they decide alike)
+            const bool need = (j == 0) ? (mx > m_ref) : (mx > m_ref + 8.0f);
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+              // rescale this warp's rows and columns of O (and l) to the new reference; the previous PV must have completed
+              pp_wait(&pv_done[X], (cnt - 1) & 1, a.trace, 14, (i * nb + j) * 2 + X);
+              tc_fence_after();
+              const float alpha = need ? fast_exp2(m_ref - mx) : 1.f;    // m_ref = -inf -> 0 (O and l are 0 then)
+              pp_rescale(t_o, alpha);
+              l_run *= alpha;
+              if (need) m_ref = mx;
+            } else if (need) {
+              m_ref = mx;                              // first block of the task
             }
-            if (c4 == (nch > 1 ? 1 : 0) && X == 0 && cnt == 0 && lane == 0) mbar_arrive(half_a);
-          }
-          l_run += ls0 + ls1;
-          // the P buffer of this tile was the A operand of the previous block's PV
-          if (cnt >= 1) pp_wait(&pv_done[X], (cnt - 1) & 1, a.trace, 15, (i * nb + j) * 2 + X);
-          // P row: a half tile holds 64 keys = 128 bytes = 8 chunks of 8 keys
+            const float nm = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            // all exponentials first, packed in registers: the wait for the P buffer (the previous block's PV, a
+            // barrier round trip through the MMA issuer) comes AFTER them, right before the first store
+            uint32_t pk[nch > 0 ? nch : 1][16];
+            float ls0 = 0.f, ls1 = 0.f;
+            take_turn();
 #pragma unroll
-          for (int c4 = 0; c4 < nch; ++c4) {
-            uint8_t* half = sPx + (c4 >> 1) * kPpTile;
+            for (int c2 = 0; c2 < nch; ++c2) {
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-              *reinterpret_cast<uint4*>(half + pp_swz(row, (c4 & 1) * 4 + ch)) =
-                  make_uint4(pk[c4][4 * ch], pk[c4][4 * ch + 1], pk[c4][4 * ch + 2], pk[c4][4 * ch + 3]);
-          }
-          fence_proxy_async_smem();                    // P visible to the tensor core (async proxy)
-          pp_trace(trw, s, 10 + 3 * X);
+              for (int c = 0; c < 16; c += 2) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(r[c2][2 * c]), sl2, nm));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(r[c2][2 * c + 1]), sl2, nm));
+                const float p2 = fast_exp2(fmaf(__uint_as_float(r[c2][2 * c + 2]), sl2, nm));
+                const float p3 = fast_exp2(fmaf(__uint_as_float(r[c2][2 * c + 3]), sl2, nm));
+                ls0 += p0 + p1;
+                ls1 += p2 + p3;
+                pk[c2][c] = pack_bf16x2(p0, p1);       // keys 2c, 2c+1 of the chunk
+                pk[c2][c + 1] = pack_bf16x2(p2, p3);
+              }
+            }
+            l_run += ls0 + ls1;
+            pass_turn();
+            // the P buffer of this tile was the A operand of the previous block's PV
+            if (cnt >= 1) pp_wait(&pv_done[X], (cnt - 1) & 1, a.trace, 15, (i * nb + j) * 2 + X);
+            // P row of this half: 64 keys = 128 bytes = 8 chunks of 8 keys
+#pragma unroll
+            for (int c2 = 0; c2 < nch; ++c2) {
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch)
+                *reinterpret_cast<uint4*>(sPh + pp_swz(row, c2 * 4 + ch)) =
+                    make_uint4(pk[c2][4 * ch], pk[c2][4 * ch + 1], pk[c2][4 * ch + 2], pk[c2][4 * ch + 3]);
+            }
+            if (nch > 0) fence_proxy_async_smem();     // P visible to the tensor core (async proxy)
+            pp_trace(trw, s, 10 + 3 * X);
           };
-          switch (min(4, (a.Lk - j * kPpBK + 31) >> 5)) {
-            case 4: block(std::integral_constant<int, 4>{}); break;
-            case 3: block(std::integral_constant<int, 3>{}); break;
+          const int nchh = min(2, max(0, ((a.Lk - j * kPpBK + 31) >> 5) - 2 * hh));
+          switch (nchh) {
             case 2: block(std::integral_constant<int, 2>{}); break;
-            default: block(std::integral_constant<int, 1>{}); break;
+            case 1: block(std::integral_constant<int, 1>{}); break;
+            default: block(std::integral_constant<int, 0>{}); break;
           }
         } else {
           if (lane == 0) mbar_arrive(&s_free[X]);
-          if (X == 0 && cnt == 0 && lane == 0) mbar_arrive(half_a);
+          take_turn();
+          pass_turn();
           // a warp without real rows must not run ahead of the others: with S released early it could arrive on
           // p_ready for block j + 1 while a live warp still owes its arrival for block j (and every warp waits for
           // every phase of pv_done, so that its parity never aliases)
@@ -497,53 +567,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // all MMAs of the task's tile have completed when its last PV has
       pp_wait(&pv_done[X], (cnt - 1) & 1, a.trace, 16, (i * nb + nb - 1) * 2 + X);
       tc_fence_after();
-      // log2-domain log-sum-exp of the row's scaled scores for the backward pass (rows Lq .. lse_ld get +inf, so
-      // that exp2(s - lse) of a padding row is 0 there without a predicate)
-      if (a.lse != nullptr && q0 + row < a.lse_ld)
-        a.lse[(static_cast<int64_t>(b) * a.H + h) * a.lse_ld + q0 + row] =
-            (live && q0 + row < a.Lq) ? m_ref + __log2f(l_run) : INFINITY;
       if (live) {
-        float o[64];
+        const float l_row = row_sum(l_run);            // both halves: the row's sum of P
+        // log2-domain log-sum-exp of the row's scaled scores for the backward pass (rows Lq .. lse_ld get +inf, so
+        // that exp2(s - lse) of a padding row is 0 there without a predicate)
+        if (hh == 0 && a.lse != nullptr && q0 + row < a.lse_ld)
+          a.lse[(static_cast<int64_t>(b) * a.H + h) * a.lse_ld + q0 + row] =
+              q0 + row < a.Lq ? m_ref + __log2f(l_row) : INFINITY;
+        float o[32];
         {
-          uint32_t a0[32], a1[32];
-          tmem_ld_32x32(t_o, a0);
-          tmem_ld_32x32(t_o + 32, a1);
+          uint32_t a0[32];
+          tmem_ld_32x32(t_o, a0);                      // this half's 32 of the 64 output columns
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) { o[c] = __uint_as_float(a0[c]); o[32 + c] = __uint_as_float(a1[c]); }
+          for (int c = 0; c < 32; ++c) o[c] = __uint_as_float(a0[c]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[X]);        // the next task may overwrite this O
-        // normalise, stage this warp's 32 rows in ITS rows of the tile's P buffer (its last reader, this task's
-        // last PV, has completed and only this warp writes these rows), then write whole 128-byte rows:
-        // lane = (row % 4, 16-byte chunk)
-        const float inv = 1.f / l_run;                 // l == 0 (all keys masked) -> NaN, as torch
+        // normalise, stage this warp's 32 rows x 64 bytes in ITS rows of its P half tile (their last reader, this
+        // task's last PV, has completed and only this warp writes them), then write 64-byte row pieces:
+        // lane = (row % 8, 16-byte chunk)
+        const float inv = 1.f / l_row;                 // l == 0 (all keys masked) -> NaN, as torch
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
+        for (int ch = 0; ch < 4; ++ch) {
           uint4 u;
           u.x = pack_bf16x2(o[8 * ch] * inv, o[8 * ch + 1] * inv);
           u.y = pack_bf16x2(o[8 * ch + 2] * inv, o[8 * ch + 3] * inv);
           u.z = pack_bf16x2(o[8 * ch + 4] * inv, o[8 * ch + 5] * inv);
           u.w = pack_bf16x2(o[8 * ch + 6] * inv, o[8 * ch + 7] * inv);
-          *reinterpret_cast<uint4*>(sPx + pp_swz(row, ch)) = u;
+          *reinterpret_cast<uint4*>(sPh + pp_swz(row, ch)) = u;
         }
         __syncwarp();
-        const int rr = lane >> 3, cc = lane & 7;
-        bf16* ob = a.out + (static_cast<int64_t>(b) * a.Lq + q0 + quarter * 32) * a.ldo + h * 64 + cc * 8;
+        const int rr = lane >> 2, cc = lane & 3;
+        bf16* ob = a.out + (static_cast<int64_t>(b) * a.Lq + q0 + quarter * 32) * a.ldo + h * 64 + hh * 32 + cc * 8;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const int rl = 4 * t + rr;
+        for (int t = 0; t < 4; ++t) {
+          const int rl = 8 * t + rr;
           if (q0 + quarter * 32 + rl < a.Lq)
             *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(rl) * a.ldo) =
-                *reinterpret_cast<const uint4*>(sPx + pp_swz(quarter * 32 + rl, cc));
+                *reinterpret_cast<const uint4*>(sPh + pp_swz(quarter * 32 + rl, cc));
         }
         __syncwarp();                                  // the staged rows are read before the next block's P overwrites them
       } else {
+        if (hh == 0 && a.lse != nullptr && q0 + row < a.lse_ld)
+          a.lse[(static_cast<int64_t>(b) * a.H + h) * a.lse_ld + q0 + row] = INFINITY;
         if (lane == 0) mbar_arrive(&o_free[X]);
       }
       if (lane == 0) mbar_arrive(&mask_free[tp]);
-      pp_trace(quarter == 0 ? tr : nullptr, i * nb + nb - 1, 14 + X);
+      pp_trace((quarter == 0 && hh == 0) ? tr : nullptr, i * nb + nb - 1, 14 + X);
     }
   }
 
@@ -595,8 +667,6 @@ extern "C" int tan_attention_bf16(const void* q, int64_t ldq, const void* k, int
   a.npairs = npairs;
   a.ntasks = static_cast<int>(ntasks);
   a.trace = debug_trace_ptr();
-  static const int flags = getenv("TAN_ATT_FLAGS") ? atoi(getenv("TAN_ATT_FLAGS")) : 1;     // A/B aid
-  a.flags = flags;
   const int grid = static_cast<int>(ntasks < num_sms() ? ntasks : num_sms());
   return launch_pdl(attention_kernel, dim3(grid), dim3(kPpThreads), kPpSmem, static_cast<cudaStream_t>(stream), 1, tmQ,
                     tmK, tmV, a);

@@ -364,6 +364,21 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One lane of the (converged) warp.  ptxas keeps the code under `if (elect_one())` on the uniform datapath: a run of
+// tcgen05.mma then issues back to back, whereas under `if (lane == 0)` every MMA is wrapped in a vote / elect loop
+// with its descriptors moved through R2UR (~50 clk per MMA in the attention kernel's issuer warp).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
