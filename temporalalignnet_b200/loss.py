@@ -590,7 +590,15 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
     n_glob = None
     will_compact = (COMPACT_COLUMNS and not (learn or thr > 0 or head) and N <= 64 and isinstance(logits_dual, LazyLogits)
                     and isinstance(logits_joint, LazyLogits))
-    if dist is not None and (SHARD_CHECK or will_compact):
+    hint = input_data.get('n_sentences_global') if isinstance(input_data, dict) else None
+    if dist is not None and hint is not None:
+        # a loader that slices ONE global batch over the ranks knows every clip's sentence count: no exchange, no
+        # host wait in the step (the per-step 4 KB gather below is a host-side rendezvous of all ranks)
+        if len(hint) != dist.get_world_size() * B:
+            raise TanError(f"input_data['n_sentences_global'] has {len(hint)} entries, expected world_size * B = "
+                           f"{dist.get_world_size() * B}")
+        n_glob = [min(int(n_), N) for n_ in hint] if will_compact else None
+    elif dist is not None and (SHARD_CHECK or will_compact):
         # the all-gathers below assume one (B_loc, N) on every rank; with real data N is each rank's own
         # pad_sequence length -- fail loudly instead of hanging in NCCL or mis-indexing columns.  The same 4 KB
         # exchange carries every clip's sentence count for the ragged-column layout.

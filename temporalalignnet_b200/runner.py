@@ -86,6 +86,8 @@ class TanStepRunner:
         self.d_vpm = self.h_vpm.to(self.device)
         self.d_tpm = self.h_tpm.to(self.device)
         self.input_data = {"start": self.batch["start"], "end": self.batch["end"], "text": self.batch["text_str"]}
+        if self.shard and os.environ.get("TAN_NO_COUNT_HINT") is None:
+            self.input_data["n_sentences_global"] = self.global_n_b    # the runner sliced ONE global batch: no exchange
         self.nce = loss_mod.prepare_nce_inputs(self.batch["start"], self.batch["end"], self.d_tpm, T, self.N,
                                                self.device, self.shard, compact=not self.flags and self.N <= 64)
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.h_video, self.h_text, self.h_vpm, self.h_tpm))

@@ -300,6 +300,24 @@ def _shape_worker(rank, world, port, ret):
                    {"logits_dual": lg, "logits_joint": lg}, args, None)
     except TanError as e:
         err = str(e)
+    # a loader that knows the global sentence counts passes them: no shape exchange (no host rendezvous) in the step.
+    # (On CPU get_loss cannot get past its first kernel, tan_pos_from_time: reaching THAT error means the exchange
+    # stage was passed without the collective.)
+    hint_ok = True
+    data_h = {"start": [[0.0]] * B, "end": [[1.0]] * B, "text": None}
+    lg_h = torch.zeros(B, 1, T, world * B, 4)
+    real_exchange = L.shard_exchange
+    L.shard_exchange = lambda *a_, **k_: (_ for _ in ()).throw(AssertionError("exchange called despite the hint"))
+    try:
+        for hint, want in (([1] * (world * B), "pos_from_time"), ([1], "n_sentences_global")):
+            try:
+                L.get_loss(dict(data_h, n_sentences_global=hint), torch.zeros(B, T, 4), emb2, None, mask2,
+                           {"logits_dual": lg_h, "logits_joint": lg_h}, args, None)
+                hint_ok = False
+            except TanError as e:
+                hint_ok = hint_ok and want in str(e)
+    finally:
+        L.shard_exchange = real_exchange
     # different clip counts are an error of their own
     err_b = ""
     try:
@@ -307,7 +325,7 @@ def _shape_worker(rank, world, port, ret):
     except TanError as e:
         err_b = str(e)
     res = [None] * world
-    dist.all_gather_object(res, (ok, "pad_text_to_global" in err, "same number of clips" in err_b))
+    dist.all_gather_object(res, (ok, "pad_text_to_global" in err, "same number of clips" in err_b, hint_ok))
     if rank == 0:
         ret["res"] = res
     dist.destroy_process_group()
