@@ -45,14 +45,6 @@ constexpr int kAttKVBytes = kAttBK * 128;     // 8 KB
 //     then waits behind issue_qk's K wait, softmax blocks lengthen to ~1.5 k clk, 188 vs 169 us per launch.
 // Ring depths (a 3-deep K ring was measured slower: 1.96 vs 1.62 ms per step at the bench shape).  The dynamic
 // segment is declared 1024-byte aligned instead of carrying an alignment slack; two CTAs per SM.
-#ifndef TAN_ATT_ELECT
-#define TAN_ATT_ELECT 1     // MMA issue under elect.sync (0: under lane == 0; A/B builds)
-#endif
-#if TAN_ATT_ELECT
-#define TAN_ATT_LEADER() elect_one()
-#else
-#define TAN_ATT_LEADER() (lane == 0)
-#endif
 #ifndef TAN_ATT_KSTAGES
 #define TAN_ATT_KSTAGES 2
 #endif
@@ -178,7 +170,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j == 0) mbar_wait(&q_full[qb], (qt >> 1) & 1);
       mbar_wait(&k_full[ks], (g / kAttKStages) & 1);
       tc_fence_after();
-      if (TAN_ATT_LEADER()) {
+      if (TAN_MMA_LEADER()) {
         const uint64_t dq = umma_desc_k_sw128(smem_u32(sQ + qb * kAttQBytes));
         const uint64_t dk = umma_desc_k_sw128(smem_u32(sK + ks * kAttKVBytes));
 #pragma unroll
@@ -200,7 +192,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j == 0 && qt >= 2) mbar_wait(&o_free[ob], ((qt >> 1) - 1) & 1);   // tile qt-2 has left this O buffer
       mbar_wait(&v_full[vs], (g / kAttVStages) & 1);
       tc_fence_after();
-      if (TAN_ATT_LEADER()) {
+      if (TAN_MMA_LEADER()) {
         const uint64_t dp = umma_desc_k_sw128(smem_u32(sP + (g & 1) * kAttQBytes));
         const uint64_t dv = umma_desc_k_sw128(smem_u32(sV + vs * kAttKVBytes));
         // 16 keys per MMA: +32 B along P's rows (K-major), +16 rows x 128 B = 2048 B in V (MN-major)

@@ -154,7 +154,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const int st = g % kBtStages;
       mbar_wait(&u_full[st], (g / kBtStages) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (TAN_MMA_LEADER()) {
         const uint8_t* slot = sStage + st * 17408;
         const uint64_t dx = umma_desc_k_sw128(smem_u32(sX));
         const uint64_t dy = umma_desc_k_sw128(smem_u32(sY));
@@ -178,7 +178,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       mbar_wait(p_ready, g & 1);                 // the bf16 tiles of block g are staged
       tc_fence_after();
-      if (lane == 0) {
+      if (TAN_MMA_LEADER()) {
         const uint8_t* slot = sStage + st * 17408;
         const uint64_t du = umma_desc_k_sw128(smem_u32(slot));                 // as MN-major B: 16 rows = 2048 B per step
         const uint64_t dw = umma_desc_k_sw128(smem_u32(slot + kBtBlkBytes));

@@ -379,6 +379,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+#ifndef TAN_MMA_ELECT
+#define TAN_MMA_ELECT 1     // 0: issue under lane == 0 (A/B builds)
+#endif
+#if TAN_MMA_ELECT
+#define TAN_MMA_LEADER() elect_one()
+#else
+#define TAN_MMA_LEADER() (lane == 0)
+#endif
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, single CTA.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {

@@ -126,7 +126,7 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (TAN_MMA_LEADER()) {
             const uint32_t sa = smem_u32(stages + stage * kLnStageBytes);
             const uint64_t da = umma_desc_k_sw128(sa);
             const uint64_t db0 = umma_desc_k_sw128(sa + kG2ABytes);

@@ -151,7 +151,7 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (TAN_MMA_LEADER()) {
             const uint64_t da = umma_desc_mn_sw128(smem_u32(smem_a + stage * kG2ABytes), kTnBoxBytes);
             const uint64_t db = umma_desc_mn_sw128(smem_u32(smem_b + stage * kG2BBytes), kTnBoxBytes);
             // 16 contraction rows per MMA = 16 x 128 B = 2048 B further into each box

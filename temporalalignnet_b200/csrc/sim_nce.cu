@@ -255,7 +255,7 @@ sim_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (tn == tn0) mbar_wait(&a_full[kb], a_phase);
             mbar_wait(&b_full[stage], phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (TAN_MMA_LEADER()) {
               const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * kG2ABytes));
               const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kG2BBytes));
 #pragma unroll

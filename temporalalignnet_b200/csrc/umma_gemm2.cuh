@@ -162,7 +162,7 @@ umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);            // A and B-half of BOTH CTAs have landed
           tc_fence_after();
-          if (lane == 0) {
+          if (TAN_MMA_LEADER()) {
             if (kb == 0) trace_evt2(tr, 4 + it * 8 + 2);
             const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kG2ABytes));
             const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kG2BBytes));
