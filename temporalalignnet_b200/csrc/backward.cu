@@ -170,31 +170,35 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __re
 #pragma unroll
     for (int i = 0; i < V * 4; ++i) { xv[i] -= mean; q += xv[i] * xv[i]; }
     const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
-    // gamma is re-read per row (L1-resident): holding it would cost 4 V registers and, with the column-sum
-    // accumulators, push the kernel from 2 CTAs per SM to 1 (measured: 3.5 -> 7.7 ms per step)
-    float gmv[V * 4];
-    if (gamma != nullptr) {
+    // the residual-stream gradient this row accumulates into: requested NOW, next to x and dy, so that its latency
+    // is not a second, serial round trip to HBM at the end of the row (ncu r02p: 43 % of the DRAM peak, the warps
+    // parked on the first use of a load)
+    float4* pd = reinterpret_cast<float4*>(dx + static_cast<int64_t>(r) * d);
+    float4 pv[V];
+    if (accumulate) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-        gmv[4 * i] = g4.x; gmv[4 * i + 1] = g4.y; gmv[4 * i + 2] = g4.z; gmv[4 * i + 3] = g4.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < V * 4; ++i) gmv[i] = 1.f;
+      for (int i = 0; i < V; ++i) pv[i] = pd[i * 32 + lane];
     }
+    // gamma is re-read per row and per 4 columns (L1-resident): holding it would cost 4 V registers and, with the
+    // column-sum accumulators, push the kernel from 2 CTAs per SM to 1 (measured: 3.5 -> 7.7 ms per step)
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < V * 4; ++i) {
-      xv[i] *= rstd;                       // xhat
-      dg[i] += gv[i] * xv[i];
-      db[i] += gv[i];
-      gv[i] *= gmv[i];                     // g
-      sg += gv[i];
-      sgx += gv[i] * xv[i];
+    for (int i = 0; i < V; ++i) {
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (gamma != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = 4 * i + k;
+        xv[e] *= rstd;                     // xhat
+        dg[e] += gv[e] * xv[e];
+        db[e] += gv[e];
+        gv[e] *= gm[k];                    // g
+        sg += gv[e];
+        sgx += gv[e] * xv[e];
+      }
     }
     const float mg = warp_sum(sg) / d, mgx = warp_sum(sgx) / d;
-    float4* pd = reinterpret_cast<float4*>(dx + static_cast<int64_t>(r) * d);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       float4 o;
@@ -203,8 +207,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const float* __re
       o.z = rstd * (gv[4 * i + 2] - mg - xv[4 * i + 2] * mgx);
       o.w = rstd * (gv[4 * i + 3] - mg - xv[4 * i + 3] * mgx);
       if (accumulate) {
-        const float4 p = pd[i * 32 + lane];
-        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        o.x += pv[i].x; o.y += pv[i].y; o.z += pv[i].z; o.w += pv[i].w;
       }
       pd[i * 32 + lane] = o;
       if (dx_bf16 != nullptr)      // the bf16 copy the following dgrad / wgrad GEMMs read (was a separate cast pass)

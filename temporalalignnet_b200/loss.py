@@ -14,6 +14,7 @@ with z = logits / 0.07, valid columns = real sentences, positives = same clip an
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Optional
 
 import torch
@@ -192,6 +193,7 @@ def padded_times(start_list, end_list, T: int, N: int, device):
     return dev[0], dev[1]
 
 
+_ROW_KILL_WARNED = False
 COMPACT_COLUMNS = os.environ.get("TAN_COMPACT_COLUMNS", "1") != "0"
 
 
@@ -666,6 +668,14 @@ def get_loss(input_data, video_seq, text_embed, video_padding_mask, text_padding
         nce.posbits = ops.agree_targets(nce.posbits, win_j, win_d, replace.to(torch.uint8).contiguous(), B, T, N, kind)
         if fill and vpm_u8 is not None:
             nce.row_kill = vpm_u8
+            global _ROW_KILL_WARNED
+            if not _ROW_KILL_WARNED:
+                _ROW_KILL_WARNED = True
+                warnings.warn("get_loss(model='init', learn_agreement=1) with a video padding mask: padded frames lose "
+                              "their own-clip entries and drop out of the row mean here; the reference keeps a padded "
+                              "frame that carries a positive with a ~6e4 loss term (a view side effect of "
+                              "train/loss.py:96-100, DESIGN.md section 2).  Loss values differ from reference runs in "
+                              "that configuration only.", stacklevel=2)
         conf_g = _gather_flat(conf, dist)
         loss_dict['confidence-ratio'] = (conf_g & valid_g).float().sum() / valid_g.float().sum()
         loss_dict['iou-threshold'] = torch.tensor(0.5, device=device)
