@@ -443,6 +443,22 @@ TAN_API int tan_optim_adamw_step(const tan_optim_tensor* table, int n_tensors, c
 TAN_API int tan_ema_update(const tan_optim_tensor* table, const int* chunk_tensor, const int64_t* chunk_start,
                            int n_chunks, int chunk_elems, double m, void* stream);
 
+/* Sliding-window alignment inference (eval/eval_zeroshot_align.py 'overlap-seq').  Stitching of :198-205: windows
+ * [W, 4] int32 = (t0, t1, n0, n1) per window (device, 16-byte aligned); blk_joint / blk_dual [W, T, N] fp32 = the last
+ * stage's own-clip cosine blocks of the batched windows (tan_own_clip_sim).  For every (sentence n, frame t):
+ *     sim_x[n, t] = (sum over the windows covering (n, t), in window order, of blk_x[w, t - t0, n - n0] / 0.07)
+ *                   / max(cover[n, t], 1e-5),      cover[n, t] = number of such windows
+ * -- bit-identical to the reference's python loop of slice additions followed by the division.  Outputs [n_text, vlen]
+ * fp32.  A long video comes in several batches of windows: accumulate != 0 continues the running (un-normalised) sums
+ * and counts a previous call left in the outputs, finalize != 0 divides (the last batch). */
+TAN_API int tan_align_stitch(const float* blk_joint, const float* blk_dual, const int* windows, int W, int T, int N,
+                             float* sim_joint, float* sim_dual, float* cover, int n_text, int vlen, int accumulate,
+                             int finalize, void* stream);
+
+/* The decision of eval/eval_zeroshot_align.py:222-238: out[n] = argmax_t softmax_t(s[n, :]), s = sim where sim != 0,
+ * -6e4 for uncovered entries; first index on ties.  sim [n_text, vlen] fp32, out [n_text] int64. */
+TAN_API int tan_align_argmax(const float* sim, int n_text, int vlen, int64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ TAN_OK = 0
 ERR_NAMES = {-1: "TAN_ERR_SHAPE", -2: "TAN_ERR_ARCH", -3: "TAN_ERR_WORKSPACE", -4: "TAN_ERR_CUDA",
              -5: "TAN_ERR_ARG"}
 ACT_NONE, ACT_QUICKGELU, ACT_RELU = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class TanError(RuntimeError):
@@ -126,6 +126,9 @@ SIGNATURES = {
                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tan_ema_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    "tan_align_stitch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tan_align_argmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tan_attention_bwd_bf16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -6,7 +6,8 @@ The reference runs every window as its own batch-1 call and, inside it, the join
 as two more passes (`train/main.py:171-189`).  Here the windows become the clips of one batch: a short last
 window is padded with masked frames and every window's sentences are padded to the longest subset with masked
 sentences (masked keys never reach the softmax, so each window's result equals its stand-alone, unmasked
-computation); the per-window similarities are the own-clip blocks (tan_own_clip_sim) of the last stage.
+computation); the per-window similarities are the own-clip blocks (tan_own_clip_sim) of the last stage, stitched by
+tan_align_stitch (overlap average, one launch per batch of windows) and decided by tan_align_argmax.
 """
 from __future__ import annotations
 
@@ -60,44 +61,53 @@ def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_e
     dev = video.device
     vlen, n_text = video.shape[0], text_embed.shape[0]
     head = bool(model.use_alignability_head)
-    sim_j = torch.zeros(n_text, vlen, dtype=torch.float32, device=dev)
-    sim_d = torch.zeros_like(sim_j)
-    cover = torch.zeros_like(sim_j)
+    sim_j = torch.empty(n_text, vlen, dtype=torch.float32, device=dev)
+    sim_d = torch.empty_like(sim_j)
+    cover = torch.empty_like(sim_j)
     a_d = torch.zeros(n_text, dtype=torch.float32, device=dev)
     a_j = torch.zeros_like(a_d)
     a_n = torch.zeros_like(a_d)
     windows = list(windows)
+    if not windows:
+        for t_ in (sim_j, sim_d, cover):
+            t_.zero_()
     for w0 in range(0, len(windows), max_windows_per_batch):
         chunk = windows[w0:w0 + max_windows_per_batch]
         W = len(chunk)
-        T = max(t1 - t0 for t0, t1, _, _ in chunk)
-        N = max(n1 - n0 for _, _, n0, n1 in chunk)
-        vb = torch.zeros(W, T, video.shape[1], dtype=torch.float32, device=dev)
-        tb = torch.zeros(W, N, text_embed.shape[1], dtype=torch.float32, device=dev)
-        vpm = torch.ones(W, T, dtype=torch.bool, device=dev)
-        tpm = torch.ones(W, N, dtype=torch.bool, device=dev)
-        for i, (t0, t1, n0, n1) in enumerate(chunk):
-            vb[i, :t1 - t0] = video[t0:t1]
-            tb[i, :n1 - n0] = text_embed[n0:n1]
-            vpm[i, :t1 - t0] = False
-            tpm[i, :n1 - n0] = False
-        out = model._forward_impl(vb, tb, vpm, tpm)
+        win = np.asarray(chunk, dtype=np.int64).reshape(W, 4)
+        T = int((win[:, 1] - win[:, 0]).max())
+        N = int((win[:, 3] - win[:, 2]).max())
+        # the windows become the clips of one batch: frame / sentence indices and padding masks built on the host in
+        # one shot, gathered on the device by two index_select calls (no per-window copies)
+        fi = win[:, 0:1] + np.arange(T)[None, :]
+        ni = win[:, 2:3] + np.arange(N)[None, :]
+        vpad, tpad = fi >= win[:, 1:2], ni >= win[:, 3:4]
+        fi_d = torch.from_numpy(np.where(vpad, 0, fi).reshape(-1)).to(dev, non_blocking=True)
+        ni_d = torch.from_numpy(np.where(tpad, 0, ni).reshape(-1)).to(dev, non_blocking=True)
+        vpm = torch.from_numpy(vpad).to(dev, non_blocking=True)
+        tpm = torch.from_numpy(tpad).to(dev, non_blocking=True)
+        vb = video.index_select(0, fi_d).view(W, T, -1).masked_fill(vpm[..., None], 0.0)
+        tb = text_embed.index_select(0, ni_d).view(W, N, -1).masked_fill(tpm[..., None], 0.0)
+        out = model._forward_impl(vb.float(), tb.float(), vpm, tpm)
         blocks = {}
         for key in ("logits_dual", "logits_joint"):
             lg: LazyLogits = out[key]
             Bv, S, Tv, d = lg.vfeat.shape
             blocks[key] = ops.own_clip_sim(lg.vfeat, lg.tfeat, lg.shared_text, Bv, S, Tv, N, d, s_first=S - 1,
-                                           s_count=1)[:, 0] / 0.07                     # [W, T, N]
-        for i, (t0, t1, n0, n1) in enumerate(chunk):
-            sim_j[n0:n1, t0:t1] += blocks["logits_joint"][i, :t1 - t0, :n1 - n0].t()
-            sim_d[n0:n1, t0:t1] += blocks["logits_dual"][i, :t1 - t0, :n1 - n0].t()
-            cover[n0:n1, t0:t1] += 1
-            if head:
-                a_d[n0:n1] += out["dual_logits_alignability"][i, :n1 - n0, 0]
-                a_j[n0:n1] += out["joint_logits_alignability"][i, 2, :n1 - n0, 0]
-                a_n[n0:n1] += 1
+                                           s_count=1).view(W, Tv, N)                   # [W, T, N] cosines
+        # stitching (eval_zeroshot_align.py:198-201): one kernel per batch of windows, sums in window order
+        win_d = torch.from_numpy(win.astype(np.int32)).to(dev, non_blocking=True)
+        last = w0 + max_windows_per_batch >= len(windows)
+        ops.align_stitch(blocks["logits_joint"], blocks["logits_dual"], win_d, sim_j, sim_d, cover, accumulate=w0 > 0,
+                         finalize=last)
+        if head:
+            # sentence n of window i -> row n0_i + n of the per-sentence accumulators (padded sentences -> weight 0)
+            keep = torch.from_numpy((~tpad).reshape(-1).astype(np.float32)).to(dev, non_blocking=True)
+            a_d.index_add_(0, ni_d, out["dual_logits_alignability"][:, :N, 0].reshape(-1).float() * keep)
+            a_j.index_add_(0, ni_d, out["joint_logits_alignability"][:, 2, :N, 0].reshape(-1).float() * keep)
+            a_n.index_add_(0, ni_d, keep)
     eps = 1e-5
-    res = {"sim-joint": sim_j / cover.clamp(min=eps), "sim-dual": sim_d / cover.clamp(min=eps), "overlap": cover}
+    res = {"sim-joint": sim_j, "sim-dual": sim_d, "overlap": cover}
     res["sim"] = (res["sim-joint"] + res["sim-dual"]) / 2
     if head:
         res["alignability-dual"] = a_d / a_n.clamp(min=eps)
@@ -107,6 +117,7 @@ def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_e
 
 def predicted_frames(sim: torch.Tensor) -> torch.Tensor:
     """Per sentence, the frame the alignment picks (eval_zeroshot_align.py:222-238: uncovered entries count as
-    -6e4, softmax over time, argmax)."""
-    s = sim.masked_fill(sim == 0, -6e4)
-    return s.softmax(-1).argmax(-1)
+    -6e4, softmax over time, argmax): tan_align_argmax, a warp per sentence."""
+    if not sim.is_cuda:
+        raise TanError("predicted_frames runs on a CUDA (sm_100a) device only; there is no CPU path")
+    return ops.align_argmax(sim.float().contiguous())

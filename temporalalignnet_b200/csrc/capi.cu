@@ -167,7 +167,7 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ in, uint4* __res
 
 using namespace tanb;
 
-extern "C" int tan_abi_version(void) { return 4; }
+extern "C" int tan_abi_version(void) { return 5; }
 
 extern "C" const char* tan_last_error_string(void) { return g_err; }
 

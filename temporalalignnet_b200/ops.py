@@ -227,6 +227,33 @@ def own_clip_sim(vfeat, tfeat, shared_text: bool, B: int, S: int, T: int, N: int
     return out
 
 
+def align_stitch(blk_joint: torch.Tensor, blk_dual: torch.Tensor, windows_i32: torch.Tensor, sim_joint: torch.Tensor,
+                 sim_dual: torch.Tensor, cover: torch.Tensor, accumulate: bool, finalize: bool) -> None:
+    """tan_align_stitch: blk_* [W, T, N] fp32 own-clip cosines of a batch of windows, windows [W, 4] int32
+    (t0, t1, n0, n1); sim_* / cover [n_text, vlen] fp32 running sums -> averages when `finalize`."""
+    _need(blk_joint, torch.float32, "align_stitch.blk_joint")
+    _need(blk_dual, torch.float32, "align_stitch.blk_dual")
+    _need(windows_i32, torch.int32, "align_stitch.windows")
+    for t in (sim_joint, sim_dual, cover):
+        _need(t, torch.float32, "align_stitch.out")
+    W, T, N = blk_joint.shape
+    n_text, vlen = sim_joint.shape
+    _launch("align", float(n_text * vlen * max(W, 1)), 1, lambda: check(lib().tan_align_stitch(
+        blk_joint.data_ptr(), blk_dual.data_ptr(), windows_i32.data_ptr(), W, T, N, sim_joint.data_ptr(),
+        sim_dual.data_ptr(), cover.data_ptr(), n_text, vlen, int(bool(accumulate)), int(bool(finalize)), _stream()),
+        "tan_align_stitch"))
+
+
+def align_argmax(sim: torch.Tensor) -> torch.Tensor:
+    """tan_align_argmax: per sentence, argmax over time of the soft-max of sim (0 = uncovered -> -6e4) -> int64 [n_text]."""
+    _need(sim, torch.float32, "align_argmax.sim")
+    n_text, vlen = sim.shape
+    out = torch.empty(n_text, dtype=torch.int64, device=sim.device)
+    _launch("align", float(n_text * vlen), 1, lambda: check(lib().tan_align_argmax(
+        sim.data_ptr(), n_text, vlen, out.data_ptr(), _stream()), "tan_align_argmax"))
+    return out
+
+
 def agree_scan(own, posbits, vpm_u8, tpm_u8, B: int, T: int, N: int, fill_max: bool):
     """tan_agree_scan -> (win [B,N,2] int32, mean_logit [B,N], max_logit [B,N])."""
     dev = own.device

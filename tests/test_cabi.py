@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.tan_abi_version() == 4
+    assert lib.tan_abi_version() == 5
     assert isinstance(lib.tan_last_error_string(), bytes)
 
 
