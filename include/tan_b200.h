@@ -132,7 +132,7 @@ TAN_API int tan_linear_res_ln_stage_bf16(const void* A, int64_t lda, const void*
  *   stage emission (each pointer optional), rows split at l_split into an "A" part (l < l_split,
  *   video tokens) and a "B" part (text tokens of the joint sequence):
  *     rowA = b * strideA + l ,  rowB = b * strideB + (l - l_split)       (strides in rows)
- *     rawA_f32[rowA] / rawB_f32[rowB]   = y
+ *     rawA_f32[rowA] / rawB_f32[rowB]   = y      (with raw_strideA / raw_strideB != 0: rows b * raw_stride + l ...)
  *     nrmA_bf16[rowA] / nrmB_bf16[rowB] = bf16(y / ||y||_2)  ; nrmA_f32 / nrmB_f32 = y / ||y||_2
  * in is fp32 (in_is_bf16 == 0) or bf16.  d % 128 == 0, d <= 1024.  eps = 1e-5 (torch default).
  * Replaces: LayerNorm at model/tfm_model.py:35,:37 and model/tan_model.py:155,:167,:174,:206,:233;
@@ -161,6 +161,8 @@ typedef struct tan_ln_args {
   void* nrmB_bf16;
   float* nrmA_f32;
   float* nrmB_f32;
+  int64_t raw_strideA;   /* row strides of rawA_f32 / rawB_f32 when they differ from strideA / strideB (0: the same): */
+  int64_t raw_strideB;   /* the training tape keeps raw features stage-major while the normalised ones keep the sink's layout */
 } tan_ln_args;
 TAN_API int tan_layernorm(const tan_ln_args* args, void* stream);
 

@@ -36,6 +36,7 @@ class LnArgs(C.Structure):
         ("rawA_f32", C.c_void_p), ("rawB_f32", C.c_void_p),
         ("nrmA_bf16", C.c_void_p), ("nrmB_bf16", C.c_void_p),
         ("nrmA_f32", C.c_void_p), ("nrmB_f32", C.c_void_p),
+        ("raw_strideA", C.c_int64), ("raw_strideB", C.c_int64),
     ]
 
 

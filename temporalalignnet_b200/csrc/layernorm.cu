@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const tan_ln_args a) {
       const int64_t srow = partA ? (static_cast<int64_t>(b) * a.strideA + l)
                                  : (static_cast<int64_t>(b) * a.strideB + (l - a.l_split));
       if (raw != nullptr) {
-        float4* p = reinterpret_cast<float4*>(raw + srow * d);
+        const int64_t rs = partA ? a.raw_strideA : a.raw_strideB;
+        const int64_t rrow = rs == 0 ? srow : (static_cast<int64_t>(b) * rs + (partA ? l : l - a.l_split));
+        float4* p = reinterpret_cast<float4*>(raw + rrow * d);
 #pragma unroll
         for (int i = 0; i < V; ++i) p[i * 32 + lane] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
       }

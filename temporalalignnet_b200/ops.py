@@ -144,14 +144,17 @@ def linear_res_ln_stage(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.T
 def layernorm(x: torch.Tensor, rows: int, d: int, gamma=None, beta=None, add=None, add_rows: int = 0,
               L_in: Optional[int] = None, L_out: Optional[int] = None, l_off: int = 0,
               out_f32=None, out_bf16=None, l_split: int = 0, strideA: int = 0, strideB: int = 0,
-              rawA=None, rawB=None, nrmA_bf16=None, nrmB_bf16=None, nrmA_f32=None, nrmB_f32=None) -> None:
+              rawA=None, rawB=None, nrmA_bf16=None, nrmB_bf16=None, nrmA_f32=None, nrmB_f32=None,
+              raw_strideA: int = 0, raw_strideB: int = 0) -> None:
     """tan_layernorm; pointer-valued keyword arguments are tensors whose data_ptr() already points at
-    the first destination row (callers pass views)."""
+    the first destination row (callers pass views).  raw_stride*: row strides of rawA / rawB when they differ
+    from strideA / strideB (0 = the same)."""
     L_in = rows if L_in is None else L_in
     L_out = L_in if L_out is None else L_out
     a = LnArgs(x.data_ptr(), int(x.dtype == torch.bfloat16), rows, d, _ptr(gamma), _ptr(beta), _ptr(add), add_rows,
                L_in, L_out, l_off, _ptr(out_f32), _ptr(out_bf16), l_split, strideA, strideB,
-               _ptr(rawA), _ptr(rawB), _ptr(nrmA_bf16), _ptr(nrmB_bf16), _ptr(nrmA_f32), _ptr(nrmB_f32))
+               _ptr(rawA), _ptr(rawB), _ptr(nrmA_bf16), _ptr(nrmB_bf16), _ptr(nrmA_f32), _ptr(nrmB_f32),
+               raw_strideA, raw_strideB)
     _launch("layernorm", float(rows) * d, 1, lambda: check(lib().tan_layernorm(C.byref(a), _stream()), "tan_layernorm"))
 
 

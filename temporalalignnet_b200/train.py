@@ -101,22 +101,13 @@ def run_encoder_stack_train(enc, x0: torch.Tensor, kpm, B: int, L: int, l_split:
             out["rawB"] = tape.rawB[s].view(-1, d)
         return out
 
-    # raw features are stage-major (stride = part length), the normalised ones keep the sink's layout; the
-    # LayerNorm kernel has ONE stride pair, so raw and normalised features are emitted by two calls when the
-    # layouts differ (S > 1); the second call re-reads the row (HBM-bound, first correct path).
+    # raw features are stage-major (stride = part length), the normalised ones keep the sink's layout: the
+    # LayerNorm kernel takes a second stride pair for the raw rows, so both are emitted by ONE pass over the row
     def ln_emit(x, gamma, beta, out_bf16, s: int) -> None:
         views = emit(s) if s >= 0 else {}
-        same = nrm_sink.strideA == l_split and (nB == 0 or nrm_sink.strideB == nB)
-        nrm = {k: v for k, v in views.items() if k.startswith("nrm")}
-        raw = {k: v for k, v in views.items() if k.startswith("raw")}
-        if s < 0 or same:
-            ops.layernorm(x, M, d, gamma=gamma, beta=beta, L_in=L, out_bf16=out_bf16, l_split=l_split,
-                          strideA=nrm_sink.strideA, strideB=nrm_sink.strideB, **views)
-        else:
-            ops.layernorm(x, M, d, gamma=gamma, beta=beta, L_in=L, out_bf16=out_bf16, l_split=l_split,
-                          strideA=nrm_sink.strideA, strideB=nrm_sink.strideB, **nrm)
-            ops.layernorm(x, M, d, gamma=gamma, beta=beta, L_in=L, l_split=l_split, strideA=l_split,
-                          strideB=max(nB, 1), **raw)
+        ops.layernorm(x, M, d, gamma=gamma, beta=beta, L_in=L, out_bf16=out_bf16, l_split=l_split,
+                      strideA=nrm_sink.strideA, strideB=nrm_sink.strideB, raw_strideA=l_split, raw_strideB=max(nB, 1),
+                      **views)
 
     x = x0
     for i, blk in enumerate(blocks):

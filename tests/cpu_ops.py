@@ -41,7 +41,7 @@ def linear(a, w, bias=None, residual=None, out_f32=None, out_bf16=None, act=0, t
 
 def layernorm(x, rows, d, gamma=None, beta=None, add=None, add_rows=0, L_in=None, L_out=None, l_off=0,
               out_f32=None, out_bf16=None, l_split=0, strideA=0, strideB=0, rawA=None, rawB=None, nrmA_bf16=None,
-              nrmB_bf16=None, nrmA_f32=None, nrmB_f32=None):
+              nrmB_bf16=None, nrmA_f32=None, nrmB_f32=None, raw_strideA=0, raw_strideB=0):
     L_in = rows if L_in is None else L_in
     L_out = L_in if L_out is None else L_out
     y = _rows(x)[:rows].float()
@@ -57,8 +57,8 @@ def layernorm(x, rows, d, gamma=None, beta=None, add=None, add_rows=0, L_in=None
     if out_bf16 is not None:
         _rows(out_bf16)[dst] = y.to(BF)
     partA = l < l_split
-    for part, raw, nb, nf, stride, off in ((partA, rawA, nrmA_bf16, nrmA_f32, strideA, 0),
-                                           (~partA, rawB, nrmB_bf16, nrmB_f32, strideB, l_split)):
+    for part, raw, nb, nf, stride, off, rstride in ((partA, rawA, nrmA_bf16, nrmA_f32, strideA, 0, raw_strideA),
+                                                    (~partA, rawB, nrmB_bf16, nrmB_f32, strideB, l_split, raw_strideB)):
         if raw is None and nb is None and nf is None:
             continue
         idx = part.nonzero().squeeze(1)
@@ -67,7 +67,7 @@ def layernorm(x, rows, d, gamma=None, beta=None, add=None, add_rows=0, L_in=None
         srow = b[idx] * stride + (l[idx] - off)
         yy = y[idx]
         if raw is not None:
-            _rows(raw)[srow] = yy
+            _rows(raw)[srow if rstride == 0 else b[idx] * rstride + (l[idx] - off)] = yy
         if nb is not None or nf is not None:
             n = yy / yy.norm(dim=-1, keepdim=True)
             if nf is not None:

@@ -48,7 +48,8 @@ def test_struct_layouts_match_header():
     from temporalalignnet_b200._lib import LnArgs, SimGeom
     assert ctypes.sizeof(SimGeom) == 40 and SimGeom.col_off.offset == 32
     # 64-bit: pointers 8-byte aligned; the header's field order packs to this size
-    assert ctypes.sizeof(LnArgs) == 152 and LnArgs.out_f32.offset == 64 and LnArgs.strideA.offset == 88
+    assert ctypes.sizeof(LnArgs) == 168 and LnArgs.out_f32.offset == 64 and LnArgs.strideA.offset == 88
+    assert LnArgs.raw_strideA.offset == 152 and LnArgs.raw_strideB.offset == 160
 
 
 def test_no_gpu_means_error_code_not_fallback(lib):
