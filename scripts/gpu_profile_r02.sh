@@ -2,7 +2,7 @@
 # ncu evidence of round 2: launch lists of one forward step and one training step, `--set full` captures of the kernels
 # that are new this round.  Usage: gpurun --timeout 1500 -- bash scripts/gpu_profile_r02.sh [tag]
 set -u
-TAG=${1:-r02p}
+TAG=${1:-r02x}
 mkdir -p gpurun_out
 NCU="ncu --clock-control none"
 echo "== launch list: forward step (2 eager steps at B=256, the second is the one to read)"
@@ -21,4 +21,10 @@ full simfused "sim_fused_kernel" 1
 full simgrad "SimGradEpi" 1
 full attnfwd "attention_kernel" 1
 full lnbwd "layernorm_bwd_kernel" 1
-ls -la gpurun_out | grep ${TAG}_prof
+full gemmlin "umma_gemm2_kernel<tanb::LinearEpi2<0>" 3
+full resln "gemm_res_ln_kernel" 1
+for f in gpurun_out/${TAG}_prof_*.ncu-rep; do python scripts/ncu_top.py $f 25 > ${f%.ncu-rep}_summary.txt 2>&1; done
+python scripts/launch_summary.py gpurun_out/${TAG}_fwd_launches.csv > gpurun_out/${TAG}_fwd_launches_summary.txt 2>&1
+python scripts/launch_summary.py gpurun_out/${TAG}_train_launches.csv > gpurun_out/${TAG}_train_launches_summary.txt 2>&1
+rm -f gpurun_out/${TAG}_prof_*.ncu-rep
+ls -la gpurun_out | grep ${TAG}_
