@@ -34,19 +34,26 @@ extern "C" int tan_linear_bf16(const void* A, int64_t lda, const void* W, int64_
   TAN_CHECK(make_tmap_2d(&tmB, W, 2, N, K, ldw, kG2BN / 2));              // MMA "B" = weights (features)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_f32 != nullptr) {
-    LinearEpi2<kModeF32> e;
-    e.M = M; e.N = N; e.f_tiles = f_tiles; e.n_tiles = f_tiles * t_tiles;
-    e.bias = bias; e.act = act; e.residual = residual; e.ldr = ldr; e.out_f32 = out_f32; e.ldo = ldo_f32;
-    e.extra_bf16 = static_cast<bf16*>(out_bf16); e.ld_extra = ldo_bf16;
-    return launch_umma_gemm2<LinearEpi2<kModeF32>>(tmA, tmB, tmA, tmA, e, e.n_tiles, K / kG2BK, st);
+    auto go = [&](auto e) {
+      e.M = M; e.N = N; e.f_tiles = f_tiles; e.n_tiles = f_tiles * t_tiles;
+      e.bias = bias; e.act = act; e.residual = residual; e.ldr = ldr; e.out_f32 = out_f32; e.ldo = ldo_f32;
+      e.extra_bf16 = static_cast<bf16*>(out_bf16); e.ld_extra = ldo_bf16;
+      return launch_umma_gemm2<decltype(e)>(tmA, tmB, tmA, tmA, e, e.n_tiles, K / kG2BK, st);
+    };
+    if (act == TAN_ACT_NONE) return go(LinearEpi2<kModeF32, TAN_ACT_NONE>{});
+    return go(LinearEpi2<kModeF32>{});
   }
-  LinearEpi2<kModeBf16> e;
-  e.M = M; e.N = N; e.f_tiles = f_tiles; e.n_tiles = f_tiles * t_tiles;
-  e.bias = bias; e.act = act; e.residual = nullptr; e.ldr = 0; e.out_f32 = nullptr; e.ldo = 0;
-  e.extra_bf16 = nullptr; e.ld_extra = 0;
   CUtensorMap tmOut;
   TAN_CHECK(make_tmap_2d(&tmOut, out_bf16, 2, M, N, ldo_bf16, 32));
-  return launch_umma_gemm2<LinearEpi2<kModeBf16>>(tmA, tmB, tmOut, tmOut, e, e.n_tiles, K / kG2BK, st);
+  auto go = [&](auto e) {
+    e.M = M; e.N = N; e.f_tiles = f_tiles; e.n_tiles = f_tiles * t_tiles;
+    e.bias = bias; e.act = act; e.residual = nullptr; e.ldr = 0; e.out_f32 = nullptr; e.ldo = 0;
+    e.extra_bf16 = nullptr; e.ld_extra = 0;
+    return launch_umma_gemm2<decltype(e)>(tmA, tmB, tmOut, tmOut, e, e.n_tiles, K / kG2BK, st);
+  };
+  if (act == TAN_ACT_QUICKGELU) return go(LinearEpi2<kModeBf16, TAN_ACT_QUICKGELU>{});
+  if (act == TAN_ACT_RELU) return go(LinearEpi2<kModeBf16, TAN_ACT_RELU>{});
+  return go(LinearEpi2<kModeBf16, TAN_ACT_NONE>{});
 }
 
 namespace {
@@ -78,17 +85,19 @@ extern "C" int tan_linear_dual_bf16(const void* A, int64_t lda, const void* W, i
     return set_error(TAN_ERR_ARG, "tan_linear_dual_bf16: bad act");
   if (bad_bf16_out(out_act, ldo_act, N) || bad_bf16_out(out_pre, ldo_pre, N))
     return set_error(TAN_ERR_SHAPE, "tan_linear_dual_bf16: outputs need 16-byte aligned bases and pitches >= N, %% 8 == 0");
-  LinearEpi2<kModeBf16Dual> e;
-  e.M = M; e.N = N; e.f_tiles = (N + kG2BN - 1) / kG2BN; e.n_tiles = e.f_tiles * ((M + 2 * kG2BM - 1) / (2 * kG2BM));
-  e.bias = bias; e.act = act; e.residual = nullptr; e.ldr = 0; e.out_f32 = nullptr; e.ldo = 0;
-  e.extra_bf16 = nullptr; e.ld_extra = 0;
   CUtensorMap tmA, tmB, tmOut, tmAux;
   TAN_CHECK(make_tmap_2d(&tmA, A, 2, M, K, lda, kG2BM));
   TAN_CHECK(make_tmap_2d(&tmB, W, 2, N, K, ldw, kG2BN / 2));
   TAN_CHECK(make_tmap_2d(&tmOut, out_act, 2, M, N, ldo_act, 32));
   TAN_CHECK(make_tmap_2d(&tmAux, out_pre, 2, M, N, ldo_pre, 32));
-  return launch_umma_gemm2<LinearEpi2<kModeBf16Dual>>(tmA, tmB, tmOut, tmAux, e, e.n_tiles, K / kG2BK,
-                                                      static_cast<cudaStream_t>(stream));
+  auto go = [&](auto e) {
+    e.M = M; e.N = N; e.f_tiles = (N + kG2BN - 1) / kG2BN; e.n_tiles = e.f_tiles * ((M + 2 * kG2BM - 1) / (2 * kG2BM));
+    e.bias = bias; e.act = act; e.residual = nullptr; e.ldr = 0; e.out_f32 = nullptr; e.ldo = 0;
+    e.extra_bf16 = nullptr; e.ld_extra = 0;
+    return launch_umma_gemm2<decltype(e)>(tmA, tmB, tmOut, tmAux, e, e.n_tiles, K / kG2BK, static_cast<cudaStream_t>(stream));
+  };
+  if (act == TAN_ACT_QUICKGELU) return go(LinearEpi2<kModeBf16Dual, TAN_ACT_QUICKGELU>{});
+  return go(LinearEpi2<kModeBf16Dual>{});
 }
 
 // Backward through c_proj AND QuickGELU in one GEMM: out = (A W^T) o gelu'(u), i.e. du = (dx W_proj) o gelu'(u)
@@ -99,7 +108,7 @@ extern "C" int tan_linear_gelu_bwd_bf16(const void* A, int64_t lda, const void* 
   TAN_CHECK(check_linear_common("tan_linear_gelu_bwd_bf16", A, lda, W, ldw, M, N, K));
   if (bad_bf16_out(out, ldo, N) || bad_bf16_out(u, ldu, N))
     return set_error(TAN_ERR_SHAPE, "tan_linear_gelu_bwd_bf16: u / out need 16-byte aligned bases and pitches >= N, %% 8 == 0");
-  LinearEpi2<kModeBf16> e;
+  LinearEpi2<kModeBf16, TAN_ACT_QUICKGELU_GRAD> e;
   e.M = M; e.N = N; e.f_tiles = (N + kG2BN - 1) / kG2BN; e.n_tiles = e.f_tiles * ((M + 2 * kG2BM - 1) / (2 * kG2BM));
   e.bias = nullptr; e.act = TAN_ACT_QUICKGELU_GRAD; e.residual = nullptr; e.ldr = 0; e.out_f32 = nullptr; e.ldo = 0;
   e.extra_bf16 = const_cast<bf16*>(static_cast<const bf16*>(u)); e.ld_extra = ldu;
@@ -107,6 +116,6 @@ extern "C" int tan_linear_gelu_bwd_bf16(const void* A, int64_t lda, const void* 
   TAN_CHECK(make_tmap_2d(&tmA, A, 2, M, K, lda, kG2BM));
   TAN_CHECK(make_tmap_2d(&tmB, W, 2, N, K, ldw, kG2BN / 2));
   TAN_CHECK(make_tmap_2d(&tmOut, out, 2, M, N, ldo, 32));
-  return launch_umma_gemm2<LinearEpi2<kModeBf16>>(tmA, tmB, tmOut, tmOut, e, e.n_tiles, K / kG2BK,
-                                                  static_cast<cudaStream_t>(stream));
+  return launch_umma_gemm2<decltype(e)>(tmA, tmB, tmOut, tmOut, e, e.n_tiles, K / kG2BK,
+                                        static_cast<cudaStream_t>(stream));
 }

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
-using TnEpi = LinearEpi2<kModeF32>;
+using TnEpi = LinearEpi2<kModeF32, TAN_ACT_NONE>;
 
 struct TnGeom {
   int R;                  // contraction length (rows of A and B)

@@ -28,8 +28,13 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
 
 __device__ __forceinline__ uint32_t swz128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-template <int MODE>
+// ACT >= 0: the activation is a compile-time constant of the instance (the epilogue of a K = 512 layer is as long
+// as its main loop: with every activation variant compiled into one body it was ~2700 instructions per tile and the
+// epilogue warps stalled on instruction fetch -- `no_inst` 17 % of all samples, ncu r02aa); ACT = -1: the runtime
+// field `act` decides (rarely used combinations).
+template <int MODE, int ACT = -1>
 struct LinearEpi2 {
+  __device__ __forceinline__ bool is_act(int x) const { return ACT >= 0 ? ACT == x : act == x; }
   // Ring depth over staging space: the MMA warp trails the TMA producer by a constant ~1.8 us (per-CTA timelines,
   // tan_debug_set_trace), so bytes in flight pace these GEMMs: the epilogue keeps ONE 4 KB staging box per warp
   // and the ring gets 6 stages (192 KB in flight per SM): +8 % over 4 stages on the K = 512 layers (same box).
@@ -107,8 +112,8 @@ struct LinearEpi2 {
           const float4 b = bvec[c * 8 + j];
           float a0 = __uint_as_float(rc[4 * j]) + b.x, a1 = __uint_as_float(rc[4 * j + 1]) + b.y;
           float a2 = __uint_as_float(rc[4 * j + 2]) + b.z, a3 = __uint_as_float(rc[4 * j + 3]) + b.w;
-          if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
-          else if (act == TAN_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          if (is_act(TAN_ACT_QUICKGELU)) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
+          else if (is_act(TAN_ACT_RELU)) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
           *reinterpret_cast<float4*>(buf + swz128(lane, j)) = make_float4(a0, a1, a2, a3);
         }
         __syncwarp();
@@ -139,7 +144,7 @@ struct LinearEpi2 {
         uint32_t packed[16];
         uint32_t packed_u[MODE == kModeBf16Dual ? 16 : 1];
         uint4 uu[4];                                    // QUICKGELU_GRAD: this row's 32 pre-activations of the chunk
-        const bool mul_grad = MODE == kModeBf16 && act == TAN_ACT_QUICKGELU_GRAD;
+        const bool mul_grad = MODE == kModeBf16 && is_act(TAN_ACT_QUICKGELU_GRAD);
         if (mul_grad) {
           const bool ok = row0 + lane < M && col0 + 32 * c < N;
           const uint4* pu = reinterpret_cast<const uint4*>(extra_bf16 + static_cast<int64_t>(row0 + lane) * ld_extra + col0 + 32 * c);
@@ -155,8 +160,8 @@ struct LinearEpi2 {
             packed_u[2 * j] = pack_bf16x2(a0, a1);
             packed_u[2 * j + 1] = pack_bf16x2(a2, a3);
           }
-          if (act == TAN_ACT_QUICKGELU) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
-          else if (act == TAN_ACT_RELU) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
+          if (is_act(TAN_ACT_QUICKGELU)) { a0 = quick_gelu(a0); a1 = quick_gelu(a1); a2 = quick_gelu(a2); a3 = quick_gelu(a3); }
+          else if (is_act(TAN_ACT_RELU)) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
           else if (mul_grad) {
             const uint4 q = uu[j >> 1];
             const float2 u01 = unpack_bf16x2((j & 1) ? q.z : q.x), u23 = unpack_bf16x2((j & 1) ? q.w : q.y);
