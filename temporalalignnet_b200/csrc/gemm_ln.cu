@@ -197,6 +197,11 @@ gemm_res_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
+        // the residual of chunk c + 2 into L1 (lane = row, one 128-byte line): the register prefetch below is issued
+        // one chunk ahead, ~0.6 of an iteration before its use, which does not cover an L2 round trip (ncu r02ad:
+        // long_sb on the FADDs that consume the residual)
+        if (c + 2 < 8 && row0 + lane < p.M)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(p.x + static_cast<int64_t>(row0 + lane) * p.ldx + col0 + 32 * (c + 2)));
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
