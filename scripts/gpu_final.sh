@@ -1,12 +1,17 @@
 #!/bin/bash
-# Round-end validation in one GPU call: the full GPU test suite, the bench line (incl. the train_step leg) and the
-# ncu launch list of one training step.  Usage: gpurun -- bash scripts/gpu_final.sh [tag]
+# what the driver runs at round end, on the final tree: GPU suite, smoke, default bench (+ reference arm)
 set -u
-TAG=${1:-r01g}
+TAG=${1:-r02ai}
 mkdir -p gpurun_out
-echo "== tests"; timeout 150 python -m pytest tests -q -m gpu -x -p no:cacheprovider > gpurun_out/${TAG}_tests.log 2>&1; echo rc=$?; tail -3 gpurun_out/${TAG}_tests.log
-echo "== bench"; timeout 150 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo rc=$?
-tail -c 900 gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
-echo "== ncu launch list of one training step"
-timeout 80 ncu --clock-control none --metrics gpu__time_duration.sum -s 1500 -c 1500 --csv --log-file gpurun_out/${TAG}_train_launches.csv \
-   python scripts/train_profile.py 256 256 0 > gpurun_out/${TAG}_train_list.log 2>&1; echo rc=$?; tail -c 300 gpurun_out/${TAG}_train_list.log
+echo "== gpu tests"; timeout 1200 python -m pytest tests -q -m gpu -x -p no:cacheprovider 2>&1 | tail -3
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+echo "== bench"; timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo rc=$?
+python - gpurun_out/${TAG}_bench.json <<'PY'
+import json, sys
+for line in open(sys.argv[1]):
+    if line.startswith("{"):
+        d = json.loads(line)
+        print({k: d.get(k) for k in ("value", "ms_per_step", "loss", "kernel_ms_per_step", "gpu_launches_per_step")})
+        print("e2e", d["e2e"], "roofline", d["roofline"]["frac"], "sim", d["roofline_sim"]["frac"], "attn", d["roofline_attention"]["frac"], "enc", d["encoder_path"]["frac"], "step", d["whole_step_tensor_frac"])
+        print("train", d["train_step"]["ms_per_step"], d["train_step"]["value"], "eager", d["eager_gpu_baseline"]["fp16_autocast"]["value"], d["eager_gpu_baseline"]["fp16_autocast_train_step"]["value"], "cpu", d["cpu_baseline"]["value"], "parity", d["loss_parity"]["rel_err"], "clk", d["clocks"])
+PY
