@@ -1,4 +1,6 @@
-"""Per-CTA timeline of one tan_attention_bf16 launch (tan_debug_set_trace).  usage: B H L"""
+"""Per-CTA timeline of one tan_attention_bf16 launch (tan_debug_set_trace).  Needs the trace build of the attention
+kernel: make -C temporalalignnet_b200/csrc variant SRC=attention NAME=trace FLAGS="-DTAN_WAIT_HINT_ALL=0 -DTAN_ATT_TRACE"
+and TAN_LIB_PATH=$PWD/temporalalignnet_b200/libtan_b200_trace.so.  usage: B H L"""
 import os, sys
 import numpy as np
 import torch

@@ -61,8 +61,13 @@ __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 1
 // 0 globaltimer, 1 start, 2 prologue done, 3 exit; block g < 10 at 8 + 10 g: +0 K issued, +1 V issued (producer),
 // +2 QK issued, +3 p_ready seen, +4 PV issued (MMA warp), +5 s_full seen, +6 S in registers, +7 P staged (softmax warp 2)
 extern __device__ long long* g_gemm_trace;
+// (compiled in with -DTAN_ATT_TRACE only -- `make variant SRC=attention NAME=trace FLAGS="-DTAN_WAIT_HINT_ALL=0
+// -DTAN_ATT_TRACE"`, then TAN_LIB_PATH=.../libtan_b200_trace.so python scripts/attn_trace.py B H L: eight predicated
+// stamp sequences per key block are instructions the softmax loop does not need)
 __device__ __forceinline__ void att_trace(long long* tr, int g, int k) {
+#ifdef TAN_ATT_TRACE
   if (tr != nullptr && g < 10) tr[8 + 10 * g + k] = clock64();
+#endif
 }
 
 __global__ void __launch_bounds__(kAttThreads, 2)
