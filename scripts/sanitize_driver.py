@@ -77,4 +77,15 @@ tok = torch.randint(0, 200, (9, 32), device=dev)
 e = w2v(input_ids=tok, attention_mask=tok != 0)["pooler_output"]
 e.sum().backward()
 torch.cuda.synchronize()
+# sliding-window alignment: batched windows, stitching + decision kernels (two batches: accumulate / finalize flags)
+import numpy as np  # noqa: E402
+from temporalalignnet_b200.align import plan_windows, predicted_frames, sliding_window_alignment  # noqa: E402
+sd3 = synth.make_state_dict(1, 3, use_alignability_head=True, seed=12)
+m3 = TemporalAligner(1, 3, random_pos_start=0, use_alignability_head=1)
+m3.load_state_dict({k: torch.from_numpy(v) for k, v in sd3.items()})
+m3 = m3.to(dev)
+wins = plan_windows(90, 32, np.linspace(1, 88, 10), np.ones(10, bool))
+res = sliding_window_alignment(m3, r(90, 1024), r(10, 512), wins, max_windows_per_batch=3)
+print("predicted frames", predicted_frames(res["sim"]).tolist())
+torch.cuda.synchronize()
 print("sanitize driver done, launches:", ops.launches())
