@@ -548,3 +548,65 @@ def get_loss_full(logits: dict, start_list, end_list, video_padding_mask, text_p
         loss = loss * nce_w + bce
     out["loss"] = loss
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Sliding-window alignment, 'overlap-seq' (eval/eval_zeroshot_align.py:126-205)
+# ------------------------------------------------------------------------------------------------
+
+def overlap_seq_windows(vlen: int, seq_len: int, text_mid_ts, tgt_aligned):
+    """The window loop of eval/eval_zeroshot_align.py:129-177, host part only: for every step the frame range
+    [step, min(vlen, step + seq_len)) and the boolean sentence mask the reference builds (:149-167), skipping the
+    steps it skips (:155-156, :176-177).  text_mid_ts = (start + end) / 2 per sentence (:134); tgt_aligned marks
+    the alignable sentences, the NON-alignable ones choose the windows (:149-154)."""
+    mid = np.asarray(text_mid_ts, dtype=np.float64)
+    aligned = np.asarray(tgt_aligned).astype(bool)
+    n_text = len(mid)
+    step = np.arange(0, vlen - seq_len // 2, seq_len // 4)                            # :129
+    out = []
+    for idx, step_ in enumerate(step):
+        na_idx = np.arange(n_text)[~aligned]                                          # :149
+        na_mid = mid[~aligned]                                                        # :150
+        in_win = np.logical_and(step_ - seq_len <= na_mid, na_mid <= step_ + seq_len + seq_len)   # :151-153
+        active = na_idx[in_win]
+        if len(active) == 0:                                                          # :155
+            continue
+        left, right = active.min(), active.max()                                      # :158-160
+        mask = np.zeros(n_text).astype(bool)
+        if idx <= 3:                                                                  # :163
+            left = 0
+        elif idx >= len(step) - 4:                                                    # :165
+            right = vlen
+        mask[left: right + 1] = True                                                  # :167
+        if np.sum(mask) == 0:                                                         # :176
+            continue
+        out.append((int(step_), int(min(vlen, step_ + seq_len)), mask))
+    return out
+
+
+def overlap_seq_alignment(sim_fn, vlen: int, n_text: int, windows, use_alignability_head: bool):
+    """The accumulation of eval/eval_zeroshot_align.py:136-205.  sim_fn(t0, t1, mask) plays get_text_visual_sim
+    (train/main.py:171-189) for one window: {'sim', 'dual-sim'} [1, S, n_active, t1 - t0] (already / 0.07) and,
+    with the head, {'alignability-dual' [1, n_active, 1], 'alignability-joint' [1, S, n_active, 1]}."""
+    eps = torch.tensor(1e-5)
+    logits, logits_dual = torch.zeros(n_text, vlen), torch.zeros(n_text, vlen)
+    overlap = torch.zeros(n_text, vlen)
+    a_dual, a_joint, text_overlap = torch.zeros(n_text), torch.zeros(n_text), torch.zeros(n_text)
+    for t0, t1, mask in windows:
+        m = torch.from_numpy(mask)
+        o = sim_fn(t0, t1, mask)
+        if use_alignability_head:                                                     # :182-187
+            a_dual[m] += o["alignability-dual"][0, :, 0]
+            a_joint[m] += o["alignability-joint"][0, 2, :, 0]
+        else:                                                                         # :188-195
+            a_dual[m] += o["dual-sim"][0, -1].max(-1).values
+            a_joint[m] += o["sim"][0, -1].max(-1).values
+        text_overlap[m] += 1
+        logits[m, t0:t1] += o["sim"][0, -1, :]                                        # :197-199
+        logits_dual[m, t0:t1] += o["dual-sim"][0, -1, :]
+        overlap[m, t0:t1] += 1
+    logits = logits.div(torch.maximum(overlap, eps))                                  # :200-201
+    logits_dual = logits_dual.div(torch.maximum(overlap, eps))
+    return {"sim-joint": logits, "sim-dual": logits_dual, "sim": (logits + logits_dual) / 2, "overlap": overlap,
+            "alignability-dual": a_dual.div(torch.maximum(text_overlap, eps)),        # :203-204
+            "alignability-joint": a_joint.div(torch.maximum(text_overlap, eps))}

@@ -23,8 +23,13 @@ from .tan_model import LazyLogits, TemporalAligner
 Window = Tuple[int, int, int, int]          # frames [t0, t1), sentences [n0, n1)
 
 
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise TanError(f"{what} runs on a CUDA (sm_100a) device only; there is no CPU path")
+
+
 def plan_windows(vlen: int, seq_len: int, text_mid_ts: Sequence[float], anchor_mask: Sequence[bool]) -> List[Window]:
-    """The window plan of eval/eval_zeroshot_align.py:128-171: windows of `seq_len` frames every seq_len/4
+    """The window plan of eval/eval_zeroshot_align.py:129-177: windows of `seq_len` frames every seq_len/4
     frames; a window's sentences are the index range spanned by the ANCHOR sentences (the reference uses the
     non-alignable ones, whose ASR timestamps do not leak ground truth) whose mid timestamp lies within
     [step - seq_len, step + 2*seq_len]; the first / last four windows extend to the first / last sentence."""
@@ -40,7 +45,9 @@ def plan_windows(vlen: int, seq_len: int, text_mid_ts: Sequence[float], anchor_m
         if idx <= 3:
             left = 0
         elif idx >= len(steps) - 4:
-            right = len(mid) - 1
+            right = min(vlen, len(mid) - 1)            # the reference's slice [left : vlen + 1] over the sentences
+        if right < left:                               # an empty sentence slice: the reference skips the window (:176)
+            continue
         out.append((int(step), int(min(vlen, step + seq_len)), left, right + 1))
     return out
 
@@ -51,11 +58,11 @@ def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_e
     """video [vlen, D_in] fp32 (CUDA), text_embed [n_text, D_text] fp32 (CUDA), windows from `plan_windows`.
 
     Returns fp32 tensors: 'sim-joint' / 'sim-dual' [n_text, vlen] = last-stage logits / 0.07 averaged over the
-    windows that cover (sentence, frame) (eval_zeroshot_align.py:198-201), 'sim' = their mean (:205),
-    'overlap' [n_text, vlen] coverage counts, and, with an alignability head, 'alignability-dual' /
-    'alignability-joint' [n_text] (joint stage index 2, :184) averaged over windows (:203-204)."""
-    if not video.is_cuda:
-        raise TanError("sliding_window_alignment runs on a CUDA (sm_100a) device only; there is no CPU path")
+    windows that cover (sentence, frame) (eval_zeroshot_align.py:197-201), 'sim' = their mean (:205),
+    'overlap' [n_text, vlen] coverage counts, and 'alignability-dual' / 'alignability-joint' [n_text] averaged over
+    the windows that hold the sentence (:203-204): the alignability head's outputs (joint stage index 2, :182-187)
+    or, for a model without the head, the sentence's largest similarity inside each window (:188-195)."""
+    _require_cuda(video, "sliding_window_alignment")
     if model.random_pos_start:
         raise TanError("sliding_window_alignment needs random_pos_start=0 (deterministic positional offsets)")
     dev = video.device
@@ -95,7 +102,7 @@ def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_e
             Bv, S, Tv, d = lg.vfeat.shape
             blocks[key] = ops.own_clip_sim(lg.vfeat, lg.tfeat, lg.shared_text, Bv, S, Tv, N, d, s_first=S - 1,
                                            s_count=1).view(W, Tv, N)                   # [W, T, N] cosines
-        # stitching (eval_zeroshot_align.py:198-201): one kernel per batch of windows, sums in window order
+        # stitching (eval_zeroshot_align.py:197-201): one kernel per batch of windows, sums in window order
         win_d = torch.from_numpy(win.astype(np.int32)).to(dev, non_blocking=True)
         last = w0 + max_windows_per_batch >= len(windows)
         ops.align_stitch(blocks["logits_joint"], blocks["logits_dual"], win_d, sim_j, sim_d, cover, accumulate=w0 > 0,
@@ -106,18 +113,24 @@ def sliding_window_alignment(model: TemporalAligner, video: torch.Tensor, text_e
             a_d.index_add_(0, ni_d, out["dual_logits_alignability"][:, :N, 0].reshape(-1).float() * keep)
             a_j.index_add_(0, ni_d, out["joint_logits_alignability"][:, 2, :N, 0].reshape(-1).float() * keep)
             a_n.index_add_(0, ni_d, keep)
+        else:
+            # no alignability head (eval_zeroshot_align.py:188-195): a sentence's score in a window is the largest
+            # similarity (logit / 0.07) over the window's real frames
+            keep = torch.from_numpy((~tpad).reshape(-1)).to(dev, non_blocking=True)
+            for key, acc in (("logits_dual", a_d), ("logits_joint", a_j)):
+                top = blocks[key].float().masked_fill(vpm[..., None], float("-inf")).amax(dim=1) * (1.0 / 0.07)
+                acc.index_add_(0, ni_d, torch.where(keep, top.reshape(-1), torch.zeros((), device=dev)))
+            a_n.index_add_(0, ni_d, keep.float())
     eps = 1e-5
     res = {"sim-joint": sim_j, "sim-dual": sim_d, "overlap": cover}
     res["sim"] = (res["sim-joint"] + res["sim-dual"]) / 2
-    if head:
-        res["alignability-dual"] = a_d / a_n.clamp(min=eps)
-        res["alignability-joint"] = a_j / a_n.clamp(min=eps)
+    res["alignability-dual"] = a_d / a_n.clamp(min=eps)
+    res["alignability-joint"] = a_j / a_n.clamp(min=eps)
     return res
 
 
 def predicted_frames(sim: torch.Tensor) -> torch.Tensor:
     """Per sentence, the frame the alignment picks (eval_zeroshot_align.py:222-238: uncovered entries count as
     -6e4, softmax over time, argmax): tan_align_argmax, a warp per sentence."""
-    if not sim.is_cuda:
-        raise TanError("predicted_frames runs on a CUDA (sm_100a) device only; there is no CPU path")
+    _require_cuda(sim, "predicted_frames")
     return ops.align_argmax(sim.float().contiguous())

@@ -336,7 +336,26 @@ def agree_scan(own, posbits, vpm_u8, tpm_u8, B, T, N, fill_max):
     return win, torch.zeros(B, N), z.max(dim=1).values
 
 
-NAMES = ["gemm_tn", "linear_dual", "linear_gelu_bwd", "embed_gather", "own_clip_sim", "agree_scan", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
+def align_stitch(blk_joint, blk_dual, windows_i32, sim_joint, sim_dual, cover, accumulate, finalize):
+    """csrc/align.cu: running sums of blk / 0.07 over the windows covering (sentence, frame), divided when `finalize`."""
+    if not accumulate:
+        for t in (sim_joint, sim_dual, cover):
+            t.zero_()
+    for w, (t0, t1, n0, n1) in enumerate(windows_i32.tolist()):
+        sim_joint[n0:n1, t0:t1] += blk_joint[w, :t1 - t0, :n1 - n0].t() / 0.07
+        sim_dual[n0:n1, t0:t1] += blk_dual[w, :t1 - t0, :n1 - n0].t() / 0.07
+        cover[n0:n1, t0:t1] += 1
+    if finalize:
+        den = cover.clamp(min=1e-5)
+        sim_joint /= den
+        sim_dual /= den
+
+
+def align_argmax(sim):
+    return torch.where(sim != 0, sim, torch.full_like(sim, -6e4)).softmax(-1).argmax(-1)
+
+
+NAMES = ["align_stitch", "align_argmax", "gemm_tn", "linear_dual", "linear_gelu_bwd", "embed_gather", "own_clip_sim", "agree_scan", "cast_bf16", "linear", "layernorm", "attention", "attention_bwd", "quickgelu_fwd", "quickgelu_bwd",
          "transpose_bf16", "colsum", "layernorm_bwd", "l2norm_bwd", "batch_sum", "sim_grad_gemm", "sim_grad_tiles",
          "pos_from_time", "sim_workspace_bytes", "sim_nce_fwd", "nce_reduce"]
 
@@ -350,6 +369,8 @@ def install(monkeypatch):
     for n in NAMES:
         monkeypatch.setattr(ops, n, getattr(me, n))
     monkeypatch.setattr(tan_model.TemporalAligner, "_check_device", lambda self, t: None)
+    from temporalalignnet_b200 import align
+    monkeypatch.setattr(align, "_require_cuda", lambda t, what: None)
 
 
 def install_plain():

@@ -14,3 +14,96 @@ def test_plan_windows_matches_reference_rules():
     assert all(t1 - t0 <= seq_len and t1 <= vlen for t0, t1, _, _ in w)
     assert w[0][2] == 0 and w[-1][3] == 14                 # first / last windows reach the first / last sentence
     assert all(n1 > n0 for _, _, n0, n1 in w)
+
+
+def _ranges_from_oracle(vlen, seq_len, mid, aligned):
+    from oracle import tan_oracle as O
+    out = []
+    for t0, t1, mask in O.overlap_seq_windows(vlen, seq_len, mid, aligned):
+        idx = np.flatnonzero(mask)
+        assert np.array_equal(idx, np.arange(idx[0], idx[-1] + 1))       # the reference's masks are contiguous ranges
+        out.append((t0, t1, int(idx[0]), int(idx[-1]) + 1))
+    return out
+
+
+def test_plan_windows_equals_the_reference_loop_on_random_videos():
+    """plan_windows vs the oracle's restatement of eval/eval_zeroshot_align.py:129-177 (mask per step), over
+    random lengths, sentence counts (also more sentences than frames), timestamps and alignable sets."""
+    from temporalalignnet_b200.align import plan_windows
+    rng = np.random.default_rng(7)
+    cases = 0
+    for _ in range(300):
+        seq_len = int(rng.choice([4, 8, 32, 64]))
+        vlen = int(rng.integers(1, 400))
+        n_text = int(rng.integers(1, 60)) if rng.random() < 0.8 else vlen + int(rng.integers(2, 30))
+        mid = np.sort(rng.uniform(-5, vlen + 5, n_text)) if rng.random() < 0.7 else rng.uniform(0, vlen, n_text)
+        aligned = rng.random(n_text) < rng.choice([0.0, 0.3, 0.7, 1.0])
+        want = _ranges_from_oracle(vlen, seq_len, mid, aligned)
+        got = plan_windows(vlen, seq_len, mid, ~aligned)
+        assert got == want, (vlen, seq_len, n_text)
+        cases += len(want)
+    assert cases > 1000
+
+
+def test_plan_windows_edge_cases():
+    from temporalalignnet_b200.align import plan_windows
+    assert plan_windows(10, 32, [1.0, 5.0], [False, False]) == []          # no anchor sentence: no window
+    assert plan_windows(10, 32, [], []) == []
+    # a video shorter than half a window has no step at all (np.arange(0, vlen - seq_len // 2, .) is empty)
+    assert plan_windows(16, 32, [3.0], [True]) == []
+    w = plan_windows(17, 32, [3.0], [True])
+    assert w == [(0, 17, 0, 1)]
+
+
+import pytest  # noqa: E402
+import torch  # noqa: E402
+
+
+@pytest.mark.parametrize("head,per_batch", [(0, 256), (1, 256), (0, 3)])
+def test_sliding_window_alignment_host_logic_vs_oracle(monkeypatch, head, per_batch):
+    """The HOST logic of sliding_window_alignment (windows batched as clips, padded frames / sentences, the
+    per-sentence accumulators with and without an alignability head, several batches of windows) with the C-ABI
+    wrappers replaced by torch stand-ins (tests/cpu_ops.py), against the oracle's restatement of the reference loop
+    (eval/eval_zeroshot_align.py:129-205) that runs every window on its own."""
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import TemporalAligner, synth
+    from temporalalignnet_b200.align import plan_windows, predicted_frames, sliding_window_alignment
+    from tests import cpu_ops
+    cpu_ops.install(monkeypatch)
+    E, D, vlen, seq_len, n_text = 1, 3, 84, 32, 9                       # last window: 20 real frames of 32
+    sd = synth.make_state_dict(E, D, use_alignability_head=bool(head), seed=5)
+    g = torch.Generator().manual_seed(6)
+    video, text = torch.randn(vlen, 1024, generator=g), torch.randn(n_text, 512, generator=g)
+    mid = np.linspace(3, 80, n_text)
+    anchors = np.ones(n_text, bool)
+    anchors[1::4] = False
+    windows = plan_windows(vlen, seq_len, mid, anchors)
+    assert any(t1 - t0 < seq_len for t0, t1, _, _ in windows) and len({n1 - n0 for _, _, n0, n1 in windows}) > 1
+    m = TemporalAligner(E, D, random_pos_start=0, use_alignability_head=head)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    # the inference forward drives two CUDA streams; on CPU the windows go through the training forward (one stream,
+    # same kernels sequence per stack, same output dict), which the stand-ins can run
+    from temporalalignnet_b200 import train
+    monkeypatch.setattr(m, "_forward_impl", lambda v, t, vpm, tpm: train.forward_train(m, v, t, vpm, tpm, None))
+    res = sliding_window_alignment(m, video, text, windows, max_windows_per_batch=per_batch)
+
+    orc = O.TanOracle(sd, E, D, use_alignability_head=head)
+
+    def sim_fn(t0, t1, mask):
+        v, t = video[None, t0:t1], text[None, torch.from_numpy(mask)]
+        o = {"sim": orc.get_text_visual_sim_joint(v, t).transpose(-1, -2) / 0.07,
+             "dual-sim": orc.get_text_visual_sim_dual(v, t).transpose(-1, -2) / 0.07}
+        if head:
+            o.update(orc.get_alignability(v, t))
+        return o
+
+    ref = O.overlap_seq_alignment(sim_fn, vlen, n_text, O.overlap_seq_windows(vlen, seq_len, mid, ~anchors), bool(head))
+    assert torch.equal(res["overlap"], ref["overlap"])
+    for k in ("sim-joint", "sim-dual", "sim"):
+        assert (res[k] - ref[k]).abs().max().item() < 0.08, k           # bf16 features: cosine error 4e-3 / 0.07
+    for k in ("alignability-dual", "alignability-joint"):
+        assert (res[k] - ref[k]).abs().max().item() < (3e-2 if head else 0.08), k
+    want = torch.where(ref["sim"] != 0, ref["sim"], torch.full_like(ref["sim"], -6e4)).argmax(-1)
+    got = predicted_frames(res["sim"])
+    top = ref["sim"].gather(1, got[:, None])[:, 0]                     # near-ties may flip under bf16: compare values
+    assert ((ref["sim"].gather(1, want[:, None])[:, 0] - top).abs() < 0.16).all()
