@@ -610,3 +610,40 @@ def overlap_seq_alignment(sim_fn, vlen: int, n_text: int, windows, use_alignabil
     return {"sim-joint": logits, "sim-dual": logits_dual, "sim": (logits + logits_dual) / 2, "overlap": overlap,
             "alignability-dual": a_dual.div(torch.maximum(text_overlap, eps)),        # :203-204
             "alignability-joint": a_joint.div(torch.maximum(text_overlap, eps))}
+
+
+def global_alignment(sim_fn, use_alignability_head: bool):
+    """The 'global' method, eval/eval_zeroshot_align.py:207-215.  sim_fn() plays get_text_visual_sim(video, text_str,
+    interpolate_from=seq_len) for the whole video (same dict as in overlap_seq_alignment)."""
+    o = sim_fn()
+    sim = o["sim"][0, -1, :]                                                          # :209
+    if use_alignability_head:                                                         # :210-212
+        a_dual, a_joint = o["alignability-dual"][0, :, 0], o["alignability-joint"][0, -1, :, 0]
+    else:                                                                             # :213-215
+        a_dual, a_joint = o["dual-sim"][0, -1].max(-1).values, o["sim"][0, -1].max(-1).values
+    return {"sim": sim, "sim-joint": sim, "sim-dual": o["dual-sim"][0, -1, :], "alignability-dual": a_dual,
+            "alignability-joint": a_joint}
+
+
+def htm_align_metrics(videos, use_alignability_head: bool):
+    """The per-video bookkeeping and the final metrics of eval/eval_zeroshot_align.py:217-249.  videos: iterable of
+    (result dict with 'sim' [n_text, vlen] and 'alignability-joint' [n_text], tgt_aligned, start, end)."""
+    from sklearn import metrics                                                       # eval_zeroshot_align.py:247
+    recall, total_sim, total_tgt = [], [], []
+    for res, tgt_aligned, start, end in videos:
+        sim = res["sim"].clone()
+        keep = torch.as_tensor(np.asarray(tgt_aligned)).bool()
+        start_al, end_al = np.asarray(start)[keep.numpy()], np.asarray(end)[keep.numpy()]     # :119-120
+        sim.masked_fill_(sim == 0, -6e4)                                              # :220
+        prob = sim.softmax(-1)
+        total_tgt.append(np.array(tgt_aligned))
+        if use_alignability_head:                                                     # :217-218, :224-226
+            total_sim.append(res["alignability-joint"].numpy())
+        else:
+            total_sim.append(sim.max(-1)[0].numpy())
+        prob = prob[keep, :]                                                          # :229
+        for i in range(prob.size(0)):                                                 # :231-234
+            s, e = math.floor(start_al[i]), math.ceil(end_al[i])
+            recall.append(s <= prob[i].argmax(-1).item() <= e)
+    total_sim, total_tgt = np.concatenate(total_sim, 0), np.concatenate(total_tgt, 0)
+    return {"Recall": np.mean(recall), "AUC": metrics.roc_auc_score(total_tgt, total_sim)}

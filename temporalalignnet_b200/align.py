@@ -134,3 +134,76 @@ def predicted_frames(sim: torch.Tensor) -> torch.Tensor:
     -6e4, softmax over time, argmax): tan_align_argmax, a warp per sentence."""
     _require_cuda(sim, "predicted_frames")
     return ops.align_argmax(sim.float().contiguous())
+
+
+@torch.no_grad()
+def global_alignment(model: TemporalAligner, video: torch.Tensor, text_embed: torch.Tensor, seq_len: int) -> dict:
+    """The 'global' method of eval/eval_zeroshot_align.py:207-215: the whole video in ONE pass, the positional table
+    of the first `seq_len` positions interpolated to `vlen` frames (get_text_visual_sim of train/main.py:171-189 with
+    `interpolate_from=seq_len`).  video [vlen, D_in], text_embed [n_text, D_text] (CUDA).  Returns fp32 tensors
+    'sim-joint' / 'sim-dual' [n_text, vlen] = last-stage logits / 0.07, 'sim' = the JOINT one (:209; this method does
+    not average the two), and 'alignability-dual' / 'alignability-joint' [n_text]: the head's outputs (dual, and the
+    LAST joint stage, :211-212) or without a head the sentence's largest similarity over the video (:214-215)."""
+    _require_cuda(video, "global_alignment")
+    v, t = video[None].float(), text_embed[None].float()
+    inv_tau = 1.0 / 0.07
+    sim_j = (model.get_text_visual_sim_joint(v, t, seq_len)[0, -1].t() * inv_tau).contiguous()
+    sim_d = (model.get_text_visual_sim_dual(v, t, seq_len)[0, -1].t() * inv_tau).contiguous()
+    res = {"sim-joint": sim_j, "sim-dual": sim_d, "sim": sim_j}
+    if model.use_alignability_head:
+        a = model.get_alignability(v, t, seq_len, None)
+        res["alignability-dual"] = a["alignability-dual"][0, :, 0].float()
+        res["alignability-joint"] = a["alignability-joint"][0, -1, :, 0].float()
+    else:
+        res["alignability-dual"] = sim_d.amax(dim=-1)
+        res["alignability-joint"] = sim_j.amax(dim=-1)
+    return res
+
+
+def roc_auc(targets, scores) -> float:
+    """Area under the ROC curve of binary `targets` against `scores` -- what sklearn.metrics.roc_auc_score returns at
+    eval/eval_zeroshot_align.py:247 -- as the Mann-Whitney statistic with tied scores counted half."""
+    y = np.asarray(targets).astype(bool).reshape(-1)
+    s = np.asarray(scores, dtype=np.float64).reshape(-1)
+    if y.shape != s.shape:
+        raise ValueError(f"roc_auc: {y.shape[0]} targets for {s.shape[0]} scores")
+    n_pos, n_neg = int(y.sum()), int((~y).sum())
+    if n_pos == 0 or n_neg == 0:
+        raise ValueError("roc_auc: only one class present in targets")
+    _, inv, cnt = np.unique(s, return_inverse=True, return_counts=True)
+    last = np.cumsum(cnt)                                   # 1-based rank of the last member of every tie group
+    rank = (last - (cnt - 1) / 2.0)[inv]                    # average rank inside the group
+    return float((rank[y].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
+class AlignmentMeter:
+    """The HTM-Align bookkeeping of eval/eval_zeroshot_align.py:217-249 over the videos of a test set: Recall = the
+    share of alignable sentences whose predicted frame lies within [floor(start), ceil(end)] (:233-236), AUC = the
+    ROC-AUC of the per-sentence alignability score against the alignable flags (:222-226, :247)."""
+
+    def __init__(self, use_alignability_head: bool):
+        self.use_alignability_head = bool(use_alignability_head)
+        self.hits: List[bool] = []
+        self.scores: List[np.ndarray] = []
+        self.targets: List[np.ndarray] = []
+
+    def update(self, result: dict, tgt_aligned: Sequence[bool], start: Sequence[float], end: Sequence[float]) -> None:
+        """`result` from sliding_window_alignment / global_alignment; tgt_aligned / start / end per sentence (frames)."""
+        sim = result["sim"].float()
+        aligned = np.asarray(tgt_aligned).astype(bool)
+        if aligned.shape[0] != sim.shape[0]:
+            raise TanError(f"AlignmentMeter: {aligned.shape[0]} sentence flags for a [{sim.shape[0]}, .] similarity")
+        frames = predicted_frames(sim).cpu().numpy()
+        if self.use_alignability_head:
+            score = result["alignability-joint"]                                           # :217-218
+        else:
+            score = torch.where(sim != 0, sim, torch.full_like(sim, -6e4)).amax(dim=-1)    # :220, :226
+        self.scores.append(score.float().cpu().numpy())
+        self.targets.append(aligned.astype(np.int64))
+        s, e = np.floor(np.asarray(start, dtype=np.float64)), np.ceil(np.asarray(end, dtype=np.float64))
+        for n in np.flatnonzero(aligned):
+            self.hits.append(bool(s[n] <= frames[n] <= e[n]))
+
+    def compute(self) -> dict:
+        return {"Recall": float(np.mean(self.hits)),
+                "AUC": roc_auc(np.concatenate(self.targets, 0), np.concatenate(self.scores, 0))}

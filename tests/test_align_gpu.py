@@ -119,3 +119,47 @@ def test_sliding_window_alignment_in_several_batches_equals_one_batch():
     assert torch.equal(one["overlap"], many["overlap"])
     for k in ("sim-joint", "sim-dual", "alignability-dual", "alignability-joint"):
         assert (one[k] - many[k]).abs().max().item() < 2e-2 * max(one[k].abs().max().item(), 1.0), k
+
+
+@pytest.mark.parametrize("head", [0, 1])
+def test_global_alignment_and_meter_vs_oracle(head):
+    """The 'global' method (one pass over the whole video, positional table interpolated from seq_len) against the
+    oracle's restatement of eval/eval_zeroshot_align.py:207-215, and the Recall / AUC bookkeeping (:217-249) with
+    the decision kernel on identical inputs."""
+    from temporalalignnet_b200 import TemporalAligner
+    from temporalalignnet_b200.align import AlignmentMeter, global_alignment
+    E, D, seq_len = 2, 3, 32
+    sd = synth.make_state_dict(E, D, use_alignability_head=bool(head), seed=13)
+    m = TemporalAligner(E, D, random_pos_start=0, use_alignability_head=head)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m = m.to(DEV)
+    orc = O.TanOracle(sd, E, D, use_alignability_head=head)
+    g = torch.Generator().manual_seed(14)
+    rng = np.random.default_rng(14)
+    meter, ref_videos = AlignmentMeter(head), []
+    for vlen, n_text in [(50, 7), (32, 5), (200, 12)]:
+        video, text = torch.randn(vlen, 1024, generator=g), torch.randn(n_text, 512, generator=g)
+
+        def sim_fn():
+            v, t = video[None], text[None]
+            o = {"sim": orc.get_text_visual_sim_joint(v, t, seq_len).transpose(-1, -2) / 0.07,
+                 "dual-sim": orc.get_text_visual_sim_dual(v, t, seq_len).transpose(-1, -2) / 0.07}
+            if head:
+                o.update(orc.get_alignability(v, t, seq_len))
+            return o
+
+        res = global_alignment(m, video.to(DEV), text.to(DEV), seq_len)
+        ref = O.global_alignment(sim_fn, bool(head))
+        assert res["sim"].shape == (n_text, vlen)
+        for k in ("sim", "sim-dual"):
+            assert (res[k].cpu() - ref[k]).abs().max().item() < 0.08, k          # cosine error 4e-3 (bf16) / 0.07
+        for k in ("alignability-dual", "alignability-joint"):
+            assert (res[k].cpu() - ref[k]).abs().max().item() < (3e-2 if head else 0.08), k
+        start = np.sort(rng.uniform(0, vlen - 6, n_text))
+        end = start + rng.uniform(1, 6, n_text)
+        aligned = rng.random(n_text) < 0.6
+        aligned[0], aligned[1] = True, False
+        meter.update({k: v.to(DEV) for k, v in ref.items()}, aligned, start, end)
+        ref_videos.append((ref, aligned, start, end))
+    got, want = meter.compute(), O.htm_align_metrics(ref_videos, bool(head))
+    assert got["Recall"] == want["Recall"] and abs(got["AUC"] - want["AUC"]) < 1e-6, (got, want)

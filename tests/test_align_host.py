@@ -107,3 +107,73 @@ def test_sliding_window_alignment_host_logic_vs_oracle(monkeypatch, head, per_ba
     got = predicted_frames(res["sim"])
     top = ref["sim"].gather(1, got[:, None])[:, 0]                     # near-ties may flip under bf16: compare values
     assert ((ref["sim"].gather(1, want[:, None])[:, 0] - top).abs() < 0.16).all()
+
+
+def test_roc_auc_equals_sklearn_with_and_without_ties():
+    metrics = pytest.importorskip("sklearn.metrics")
+    from temporalalignnet_b200.align import roc_auc
+    rng = np.random.default_rng(3)
+    for n in (2, 5, 64, 1000):
+        for ties in (False, True):
+            y = rng.random(n) < 0.4
+            y[0], y[1] = True, False
+            s = rng.integers(0, 6, n).astype(np.float64) if ties else rng.normal(size=n)
+            assert abs(roc_auc(y, s) - metrics.roc_auc_score(y, s)) < 1e-12
+    with pytest.raises(ValueError):
+        roc_auc([1, 1, 1], [0.1, 0.2, 0.3])
+
+
+@pytest.mark.parametrize("head", [0, 1])
+def test_global_alignment_and_meter_host_logic_vs_oracle(monkeypatch, head):
+    """global_alignment (one pass, interpolated positional table) and AlignmentMeter (Recall / AUC bookkeeping) with
+    the stand-in kernels, against the oracle's restatement of eval/eval_zeroshot_align.py:207-249, over three videos
+    (two 'global', one 'overlap-seq' result)."""
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import TemporalAligner, synth, train
+    from temporalalignnet_b200.align import (AlignmentMeter, global_alignment, plan_windows,
+                                             sliding_window_alignment)
+    from tests import cpu_ops
+    cpu_ops.install(monkeypatch)
+    E, D, seq_len = 1, 3, 32
+    sd = synth.make_state_dict(E, D, use_alignability_head=bool(head), seed=8)
+    m = TemporalAligner(E, D, random_pos_start=0, use_alignability_head=head)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    monkeypatch.setattr(m, "_forward_impl", lambda v, t, vpm, tpm: train.forward_train(m, v, t, vpm, tpm, None))
+    orc = O.TanOracle(sd, E, D, use_alignability_head=head)
+    g = torch.Generator().manual_seed(9)
+    rng = np.random.default_rng(9)
+    meter, ref_videos = AlignmentMeter(head), []
+    for vi, (vlen, n_text) in enumerate([(50, 7), (32, 5), (70, 8)]):
+        video, text = torch.randn(vlen, 1024, generator=g), torch.randn(n_text, 512, generator=g)
+        start = np.sort(rng.uniform(0, vlen - 6, n_text))
+        end = start + rng.uniform(1, 6, n_text)
+        aligned = rng.random(n_text) < 0.6
+        aligned[0], aligned[1] = True, False
+
+        def sim_fn(t0=0, t1=vlen, mask=np.ones(n_text, bool), interp=seq_len):
+            v, t = video[None, t0:t1], text[None, torch.from_numpy(mask)]
+            o = {"sim": orc.get_text_visual_sim_joint(v, t, interp).transpose(-1, -2) / 0.07,
+                 "dual-sim": orc.get_text_visual_sim_dual(v, t, interp).transpose(-1, -2) / 0.07}
+            if head:
+                o.update(orc.get_alignability(v, t, interp))
+            return o
+
+        if vi < 2:
+            res = global_alignment(m, video, text, seq_len)
+            ref = O.global_alignment(sim_fn, bool(head))
+            assert res["sim"] is res["sim-joint"]
+        else:
+            mid = (start + end) / 2
+            res = sliding_window_alignment(m, video, text, plan_windows(vlen, seq_len, mid, ~aligned))
+            ref = O.overlap_seq_alignment(lambda t0, t1, mask: sim_fn(t0, t1, mask, None), vlen, n_text,
+                                          O.overlap_seq_windows(vlen, seq_len, mid, aligned), bool(head))
+        for k in ("sim", "sim-dual"):
+            assert (res[k] - ref[k]).abs().max().item() < 0.08, (vi, k)
+        for k in ("alignability-dual", "alignability-joint"):
+            assert (res[k] - ref[k]).abs().max().item() < (3e-2 if head else 0.08), (vi, k)
+        # the bookkeeping itself is compared on IDENTICAL inputs (the oracle's fp32 result), so that a near-tie
+        # between two frames under bf16 cannot flip a hit
+        meter.update(ref, aligned, start, end)
+        ref_videos.append((ref, aligned, start, end))
+    got, want = meter.compute(), O.htm_align_metrics(ref_videos, bool(head))
+    assert got["Recall"] == want["Recall"] and abs(got["AUC"] - want["AUC"]) < 1e-12, (got, want)
