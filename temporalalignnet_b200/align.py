@@ -207,3 +207,41 @@ class AlignmentMeter:
     def compute(self) -> dict:
         return {"Recall": float(np.mean(self.hits)),
                 "AUC": roc_auc(np.concatenate(self.targets, 0), np.concatenate(self.scores, 0))}
+
+
+@torch.no_grad()
+def evaluate_alignment(model: TemporalAligner, samples, seq_len: int, method: str = "overlap-seq", embed_text=None,
+                       max_windows_per_batch: int = 256) -> dict:
+    """The loop of `test_alignment_htm` (eval/eval_zeroshot_align.py:97-252) over an iterable of HTM-Align samples
+    as its loader yields them (:63-78): 'video' [vlen, D_in] (or [1, vlen, D_in]), 'start' / 'end' [n_text] in
+    frames, 'aligned' [n_text] flags and either 'text_embed' [n_text, D_text] or 'str' (sentences) together with
+    `embed_text(list of str) -> [n_text, D_text]` (the tokenizer + `model.lang_model` of train/main.py:172-175).
+    method 'overlap-seq' (:127-205; the windows follow the NON-alignable sentences, :145-154) or 'global'
+    (:207-215).  Returns {'Recall', 'AUC'} (:249)."""
+    if method not in ("overlap-seq", "global"):
+        raise TanError(f"evaluate_alignment: unknown method {method!r} (overlap-seq | global)")
+    dev = next(model.parameters()).device
+    meter = AlignmentMeter(model.use_alignability_head)
+    for sample in samples:
+        video = torch.as_tensor(sample["video"])
+        video = (video[0] if video.dim() == 3 else video).to(dev).float()
+        if "text_embed" in sample:
+            text = torch.as_tensor(sample["text_embed"])
+        elif embed_text is not None:
+            text = embed_text(list(sample["str"]))
+        else:
+            raise TanError("evaluate_alignment: a sample needs 'text_embed', or 'str' plus an embed_text callable")
+        text = text.to(dev).float()
+        start = torch.as_tensor(sample["start"]).reshape(-1).double().cpu().numpy()
+        end = torch.as_tensor(sample["end"]).reshape(-1).double().cpu().numpy()
+        aligned = torch.as_tensor(sample["aligned"]).reshape(-1).cpu().numpy().astype(bool)
+        if not (len(start) == len(end) == len(aligned) == text.shape[0]):
+            raise TanError(f"evaluate_alignment: {text.shape[0]} sentences, {len(start)} / {len(end)} timestamps, "
+                           f"{len(aligned)} flags")
+        if method == "overlap-seq":
+            windows = plan_windows(video.shape[0], seq_len, (start + end) / 2, ~aligned)
+            res = sliding_window_alignment(model, video, text, windows, max_windows_per_batch)
+        else:
+            res = global_alignment(model, video, text, seq_len)
+        meter.update(res, aligned, start, end)
+    return meter.compute()

@@ -177,3 +177,52 @@ def test_global_alignment_and_meter_host_logic_vs_oracle(monkeypatch, head):
         ref_videos.append((ref, aligned, start, end))
     got, want = meter.compute(), O.htm_align_metrics(ref_videos, bool(head))
     assert got["Recall"] == want["Recall"] and abs(got["AUC"] - want["AUC"]) < 1e-12, (got, want)
+
+
+@pytest.mark.parametrize("method", ["overlap-seq", "global"])
+def test_evaluate_alignment_loop_vs_oracle(monkeypatch, method):
+    """evaluate_alignment == the oracle's composition of the reference's loop (eval_zeroshot_align.py:97-252) on a
+    small synthetic test set; the sentences of a video are separated well enough for bf16 not to flip a decision."""
+    from oracle import tan_oracle as O
+    from temporalalignnet_b200 import TemporalAligner, synth, train
+    from temporalalignnet_b200.align import evaluate_alignment
+    from tests import cpu_ops
+    cpu_ops.install(monkeypatch)
+    E, D, seq_len = 1, 1, 32
+    sd = synth.make_state_dict(E, D, seed=21)
+    m = TemporalAligner(E, D, random_pos_start=0)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    monkeypatch.setattr(m, "_forward_impl", lambda v, t, vpm, tpm: train.forward_train(m, v, t, vpm, tpm, None))
+    orc = O.TanOracle(sd, E, D)
+    g = torch.Generator().manual_seed(22)
+    rng = np.random.default_rng(22)
+    samples, ref_videos = [], []
+    for vlen, n_text in [(48, 6), (64, 9), (40, 4)]:
+        video, text = torch.randn(vlen, 1024, generator=g), torch.randn(n_text, 512, generator=g)
+        start = np.sort(rng.uniform(0, vlen - 6, n_text))
+        end = start + rng.uniform(1, 6, n_text)
+        aligned = rng.random(n_text) < 0.6
+        aligned[0], aligned[1] = True, False
+        samples.append({"video": video[None], "str": [f"s{i}" for i in range(n_text)], "text_embed_": text,
+                        "start": torch.tensor(start), "end": torch.tensor(end), "aligned": torch.tensor(aligned)})
+
+        def sim_fn(t0=0, t1=vlen, mask=np.ones(n_text, bool), interp=seq_len, video=video, text=text):
+            v, t = video[None, t0:t1], text[None, torch.from_numpy(mask)]
+            return {"sim": orc.get_text_visual_sim_joint(v, t, interp).transpose(-1, -2) / 0.07,
+                    "dual-sim": orc.get_text_visual_sim_dual(v, t, interp).transpose(-1, -2) / 0.07}
+
+        if method == "global":
+            ref = O.global_alignment(sim_fn, False)
+        else:
+            ref = O.overlap_seq_alignment(lambda t0, t1, mask: sim_fn(t0, t1, mask, None), vlen, n_text,
+                                          O.overlap_seq_windows(vlen, seq_len, (start + end) / 2, aligned), False)
+        ref_videos.append((ref, aligned, start, end))
+    by_str = {tuple(s["str"]): s["text_embed_"] for s in samples}
+    got = evaluate_alignment(m, samples, seq_len, method, embed_text=lambda strs: by_str[tuple(strs)])
+    want = O.htm_align_metrics(ref_videos, False)
+    # decisions: allow one sentence of the 11 alignable ones to flip under bf16 features; scores: AUC over 19 points
+    n_al = sum(int(a.sum()) for _, a, _, _ in ref_videos)
+    assert abs(got["Recall"] - want["Recall"]) <= 1.0 / n_al + 1e-9, (got, want)
+    assert abs(got["AUC"] - want["AUC"]) < 0.05, (got, want)
+    with pytest.raises(Exception):
+        evaluate_alignment(m, samples, seq_len, "nearest")
